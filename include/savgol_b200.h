@@ -1,0 +1,309 @@
+/*
+ * savgol_b200.h -- C ABI of libsavgol_b200.so, the B200-native (sm_100a CUDA)
+ * Savitzky-Golay filtering engine.
+ *
+ * Part 1 is the drop-in boundary: the exact symbols, struct layouts, argument
+ * meanings and error conventions of the reference library
+ * (Tugbars/Savitzky-Golay-Filter, include/iterative/{savgolFilter,savgol_stream,
+ * savgol2d}.h).  Code written against the reference links against this library
+ * unchanged; every apply runs on the GPU.  Pointers passed to apply functions may be
+ * device pointers (used in place, zero copy) or host pointers (staged through the GPU;
+ * pinned host memory is streamed in overlapping chunks).
+ *
+ * Part 2 holds the extensions the BASELINE configs need and the reference lacks:
+ * batched 1D / 2D entry points, explicit halos for partitioned signals, the
+ * multi-channel chunked stream, stream/device control.
+ *
+ * Each declaration cites the reference interface it replaces (path:line inside the
+ * reference repository).  There is no CPU fallback: without a CUDA device every
+ * apply function fails (-1 / 0) and prints a diagnostic.
+ */
+#ifndef SAVGOL_B200_H
+#define SAVGOL_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ======================================================================== */
+/* Part 1a -- 1D batch filter   (ref: include/iterative/savgolFilter.h)      */
+/* ======================================================================== */
+
+/* ref: savgolFilter.h:39-48 */
+#define SAVGOL_MAX_HALF_WINDOW 32
+#define SAVGOL_MAX_WINDOW (2 * SAVGOL_MAX_HALF_WINDOW + 1)
+#define SAVGOL_MAX_POLY_ORDER 10
+#define SAVGOL_MAX_DERIVATIVE 4
+
+/* ref: savgolFilter.h:63-68.  Edge treatment of savgol_apply(). */
+typedef enum {
+    SAVGOL_BOUNDARY_POLYNOMIAL = 0, /* asymmetric least-squares fits on the first/last 2n+1 samples */
+    SAVGOL_BOUNDARY_REFLECT,        /* half-sample symmetric:  d1 d0 | d0 d1 d2 ...  */
+    SAVGOL_BOUNDARY_PERIODIC,       /* wrap-around:            dL-1 | d0 d1 ...      */
+    SAVGOL_BOUNDARY_CONSTANT        /* edge replication:       d0 d0 | d0 d1 ...     */
+} SavgolBoundaryMode;
+
+/* ref: savgolFilter.h:92-98.  sizeof == 12. */
+typedef struct {
+    uint8_t half_window;  /* n, window = 2n+1, 1..32                       */
+    uint8_t poly_order;   /* m < 2n+1, <= 10                               */
+    uint8_t derivative;   /* d <= min(m, 4); 0 = smoothing                 */
+    float time_step;      /* dt > 0; outputs are scaled by 1 / dt^d        */
+    SavgolBoundaryMode boundary;
+} SavgolConfig;
+
+/* ref: savgolFilter.h:107-113.  sizeof == 8600; the fields are public and read by
+ * callers (tests, the coefficient export tool), so the layout is ABI.  The object
+ * returned by savgol_create() carries private device state behind this prefix. */
+typedef struct SavgolFilter {
+    SavgolConfig config;
+    int window_size;                                               /* 2n+1        */
+    float dt_scale;                                                /* dt^d        */
+    float center_weights[SAVGOL_MAX_WINDOW];                       /* target t=0  */
+    float edge_weights[SAVGOL_MAX_HALF_WINDOW][SAVGOL_MAX_WINDOW]; /* row e: t=n-e */
+} SavgolFilter;
+
+/* ref: savgolFilter.h:130 / src/savgolFilter.c:688-718.  Validates, computes the fp32
+ * GenFact / Gram-polynomial weight tables on the host (bit-identical to the reference).
+ * NULL + one line on stderr for an invalid configuration.  Not thread-safe. */
+SavgolFilter *savgol_create(const SavgolConfig *config);
+
+/* ref: savgolFilter.h:137.  NULL is a no-op. */
+void savgol_destroy(SavgolFilter *filter);
+
+/* ref: savgolFilter.h:152-153 / src/savgolFilter.c:743-804.
+ * output[j] = (1/dt^d) * sum_k w[k] * input[j-n+k]; edges per config.boundary.
+ * Returns 0, or -1 (+ stderr) for NULL arguments or length < 2n+1.
+ * output == input is allowed and yields the out-of-place result (the reference's own
+ * in-place result is order-dependent; see DESIGN.md "in-place").  Thread-safe. */
+int savgol_apply(const SavgolFilter *filter, const float *input, float *output, size_t length);
+
+/* ref: savgolFilter.h:181-184 / src/savgolFilter.c:877-934.  Element i lives at
+ * base + i*stride + offset (bytes).  Always polynomial edges (as the reference).
+ * Returns 0, or -1 silently for NULL / count < 2n+1. */
+int savgol_apply_strided(const SavgolFilter *filter,
+                         const void *input, size_t in_stride, size_t in_offset,
+                         void *output, size_t out_stride, size_t out_offset,
+                         size_t count);
+
+/* ref: savgolFilter.h:201-203 / src/savgolFilter.c:821-850.  Interior only:
+ * output[j] is centred on input[j+n]; returns input_length-2n, or 0 on error. */
+size_t savgol_apply_valid(const SavgolFilter *filter,
+                          const float *input, size_t input_length, float *output);
+
+/* ref: savgolFilter.h:210-222 */
+#define SAVGOL_SMOOTH(half_win, order) \
+    (SavgolConfig){ .half_window = (half_win), .poly_order = (order), .derivative = 0, \
+                    .time_step = 1.0f, .boundary = SAVGOL_BOUNDARY_POLYNOMIAL }
+#define SAVGOL_DERIV1(half_win, order, dt) \
+    (SavgolConfig){ .half_window = (half_win), .poly_order = (order), .derivative = 1, \
+                    .time_step = (dt), .boundary = SAVGOL_BOUNDARY_POLYNOMIAL }
+#define SAVGOL_DERIV2(half_win, order, dt) \
+    (SavgolConfig){ .half_window = (half_win), .poly_order = (order), .derivative = 2, \
+                    .time_step = (dt), .boundary = SAVGOL_BOUNDARY_POLYNOMIAL }
+
+/* ======================================================================== */
+/* Part 1b -- single-channel stream (ref: include/iterative/savgol_stream.h) */
+/* ======================================================================== */
+
+/* ref: savgol_stream.h:29-37.  sizeof == 296, caller-allocatable, so layout is ABI.
+ * The scalar one-sample-at-a-time API is host arithmetic by nature (one sample in,
+ * at most n+1 samples out); the GPU path for streaming is savgol_mcstream_* below. */
+typedef struct SavgolStream {
+    const SavgolFilter *filter;
+    float buffer[SAVGOL_MAX_WINDOW];
+    int write_pos;
+    size_t samples_received;
+    size_t samples_output;
+    bool owns_filter;
+    float dt_inv;
+} SavgolStream;
+
+SavgolStream *savgol_stream_create(const SavgolConfig *config);              /* ref: savgol_stream.h:49  */
+int savgol_stream_init(SavgolStream *stream, const SavgolFilter *filter);     /* ref: savgol_stream.h:58  */
+void savgol_stream_destroy(SavgolStream *stream);                             /* ref: savgol_stream.h:64  */
+void savgol_stream_reset(SavgolStream *stream);                               /* ref: savgol_stream.h:70  */
+float savgol_stream_push(SavgolStream *stream, float sample, bool *output_valid);           /* :84     */
+int savgol_stream_push_full(SavgolStream *stream, float sample, float *output, int max_outputs); /* :95-96 */
+int savgol_stream_flush(SavgolStream *stream, float *output, int max_count);                /* :106    */
+int savgol_stream_flush_leading(SavgolStream *stream, float *output, int max_count);        /* :116    */
+bool savgol_stream_ready(const SavgolStream *stream);                                       /* :122    */
+size_t savgol_stream_latency(const SavgolStream *stream);                                   /* :123    */
+size_t savgol_stream_buffered(const SavgolStream *stream);                                  /* :124    */
+size_t savgol_stream_samples_received(const SavgolStream *stream);                          /* :125    */
+size_t savgol_stream_samples_output(const SavgolStream *stream);                            /* :126    */
+
+/* ======================================================================== */
+/* Part 1c -- 2D filter        (ref: include/iterative/savgol2d.h)           */
+/* ======================================================================== */
+
+#define SAVGOL2D_MAX_HALF_WINDOW 16 /* ref: savgol2d.h:64 */
+#define SAVGOL2D_MAX_POLY_ORDER 6   /* ref: savgol2d.h:67 */
+#define SAVGOL2D_MAX_TERMS 28       /* ref: savgol2d.h:70 */
+#define SAVGOL2D_MAX_WINDOW_AREA ((2 * SAVGOL2D_MAX_HALF_WINDOW + 1) * (2 * SAVGOL2D_MAX_HALF_WINDOW + 1))
+
+/* ref: savgol2d.h:82-90.  sizeof == 16. */
+typedef struct {
+    uint8_t half_window_x; /* columns */
+    uint8_t half_window_y; /* rows    */
+    uint8_t poly_order;    /* total degree: terms x^i y^j with i+j <= order */
+    uint8_t deriv_x;
+    uint8_t deriv_y;
+    float delta_x;
+    float delta_y;
+} Savgol2DConfig;
+
+/* ref: savgol2d.h:95-103.  sizeof == 48; `weights` is public (tests read it). */
+typedef struct Savgol2DFilter {
+    Savgol2DConfig config;
+    int window_width;
+    int window_height;
+    int window_area;
+    int num_terms;
+    float scale;    /* 1 / (delta_x^dx * delta_y^dy) */
+    float *weights; /* [window_height][window_width], host memory */
+} Savgol2DFilter;
+
+/* ref: savgol2d.h:108-112 */
+typedef enum {
+    SAVGOL2D_BOUNDARY_VALID = 0, /* interior written at offset (ny,nx); border untouched */
+    SAVGOL2D_BOUNDARY_CONSTANT,  /* clamp to edge pixel  */
+    SAVGOL2D_BOUNDARY_REFLECT    /* half-sample symmetric */
+} Savgol2DBoundary;
+
+Savgol2DFilter *savgol2d_create(const Savgol2DConfig *config); /* ref: savgol2d.h:126 */
+void savgol2d_destroy(Savgol2DFilter *filter);                  /* ref: savgol2d.h:132 */
+
+/* ref: savgol2d.h:154-156 / src/savgol2d.c:356-396.  Strides in elements.
+ * 0 ok; -1 for NULL or a non-positive valid size. */
+int savgol2d_apply_valid(const Savgol2DFilter *filter,
+                         const float *input, int rows, int cols, int in_stride,
+                         float *output, int out_stride);
+
+/* ref: savgol2d.h:171-174 / src/savgol2d.c:398-456 */
+int savgol2d_apply(const Savgol2DFilter *filter,
+                   const float *input, int rows, int cols, int in_stride,
+                   float *output, int out_stride, Savgol2DBoundary boundary);
+
+/* ref: savgol2d.h:195-241 / src/savgol2d.c:462-618.  Host-pointer or device-pointer
+ * images; each requested component is one filter create + apply, as in the reference. */
+int savgol2d_gradient(int half_win_x, int half_win_y, int poly_order,
+                      const float *input, int rows, int cols, int stride,
+                      float *grad_x, float *grad_y,
+                      float delta_x, float delta_y, Savgol2DBoundary boundary);
+int savgol2d_hessian(int half_win_x, int half_win_y, int poly_order,
+                     const float *input, int rows, int cols, int stride,
+                     float *hess_xx, float *hess_xy, float *hess_yy,
+                     float delta_x, float delta_y, Savgol2DBoundary boundary);
+int savgol2d_laplacian(int half_win_x, int half_win_y, int poly_order,
+                       const float *input, int rows, int cols, int stride,
+                       float *output,
+                       float delta_x, float delta_y, Savgol2DBoundary boundary);
+
+/* ref: savgol2d.h:250-264 */
+static inline void savgol2d_valid_size(const Savgol2DFilter *filter, int in_rows, int in_cols,
+                                       int *out_rows, int *out_cols)
+{
+    *out_rows = in_rows - 2 * filter->config.half_window_y;
+    *out_cols = in_cols - 2 * filter->config.half_window_x;
+}
+static inline int savgol2d_num_terms(int poly_order)
+{
+    return (poly_order + 1) * (poly_order + 2) / 2;
+}
+bool savgol2d_config_valid(const Savgol2DConfig *config); /* ref: savgol2d.h:269 */
+
+/* ======================================================================== */
+/* Part 2 -- extensions (no reference counterpart; same style)               */
+/* ======================================================================== */
+
+/* Library / device control ------------------------------------------------ */
+
+/* ABI version of this header (major*100+minor). */
+int savgol_b200_version(void);
+/* 1 when a CUDA device of compute capability 10.x is usable in this process. */
+int savgol_b200_device_ok(void);
+/* All subsequent launches of the calling thread go to `cuda_stream` (a cudaStream_t
+ * cast to void*; NULL = the legacy default stream).  Device-pointer calls are then
+ * asynchronous with respect to the host; host-pointer calls always complete before
+ * returning. */
+void savgol_b200_set_stream(void *cuda_stream);
+void *savgol_b200_get_stream(void);
+/* Number of kernel launches issued by this library in this process so far. */
+unsigned long long savgol_b200_launch_count(void);
+/* Arithmetic flavour: 0 (default) = FMA chains, within 1e-6*max|x|/dt^d of the
+ * reference; 1 = "exact": the reference's own summation order with unfused
+ * multiply/add, bit-identical to the reference C code (slower; for verification). */
+void savgol_b200_set_exact(int exact);
+int savgol_b200_get_exact(void);
+
+/* 1D batch ---------------------------------------------------------------- */
+
+/* `n_signals` independent signals of `length` samples; signal r starts at
+ * input + r*in_pitch (pitches in elements).  Equivalent to the caller's loop over
+ * savgol_apply() (the reference's only notion of a batch), one launch.
+ * Returns 0 / -1 like savgol_apply(). */
+int savgol_apply_batch(const SavgolFilter *filter, const float *input, float *output,
+                       size_t n_signals, size_t length, size_t in_pitch, size_t out_pitch);
+
+/* One contiguous slice [0,length) of a longer signal whose neighbours live elsewhere
+ * (another GPU, another buffer).  left_halo holds the n samples preceding input[0]
+ * (chronological order), right_halo the n samples following input[length-1]; either
+ * may be NULL, in which case that side is a true signal end and is treated per
+ * config.boundary (PERIODIC is not allowed with a NULL halo on only one side).
+ * This is the per-GPU piece of a partitioned long signal: the caller exchanges the
+ * n-sample halos (NVLink P2P / NCCL) and every slice is then independent. */
+int savgol_apply_halo(const SavgolFilter *filter, const float *input, float *output, size_t length,
+                      const float *left_halo, const float *right_halo);
+
+/* 2D batch ---------------------------------------------------------------- */
+
+/* `n_images` images, image i at input + i*in_image_pitch (elements). */
+int savgol2d_apply_batch(const Savgol2DFilter *filter,
+                         const float *input, int rows, int cols, int in_stride, size_t in_image_pitch,
+                         float *output, int out_stride, size_t out_image_pitch,
+                         size_t n_images, Savgol2DBoundary boundary);
+
+/* Multi-channel chunked stream ------------------------------------------- */
+
+/* `channels` independent streams advanced in lockstep, one chunk of K samples per
+ * channel per call.  Per channel the semantics are exactly those of the reference's
+ * savgol_stream_push_full()/savgol_stream_flush() sequence (src/savgol_stream.c:180-252):
+ * fixed latency of half_window samples, polynomial leading/trailing edges, boundary
+ * mode ignored.  Carry state (the last 2n samples per channel) lives in device memory. */
+typedef struct SavgolMCStream SavgolMCStream;
+
+SavgolMCStream *savgol_mcstream_create(const SavgolConfig *config, size_t channels);
+void savgol_mcstream_destroy(SavgolMCStream *s);
+void savgol_mcstream_reset(SavgolMCStream *s);
+
+/* Pushes chunk_len samples per channel (channel c at input + c*in_pitch) and writes
+ * that channel's new outputs, in chronological order, to output + c*out_pitch.
+ * Returns the number of outputs produced per channel: 0 while fewer than 2n+1 samples
+ * have been received, received-n on the call that crosses 2n+1, chunk_len afterwards;
+ * -1 on error.  out_pitch must be >= chunk_len + half_window. */
+long long savgol_mcstream_push(SavgolMCStream *s, const float *input, size_t in_pitch,
+                               size_t chunk_len, float *output, size_t out_pitch);
+
+/* Writes the final half_window outputs per channel (trailing edge) to
+ * output + c*out_pitch; returns half_window, 0 if the window never filled, -1 on error.
+ * Does not consume state (as the reference's flush). */
+long long savgol_mcstream_flush(SavgolMCStream *s, float *output, size_t out_pitch);
+
+size_t savgol_mcstream_channels(const SavgolMCStream *s);
+size_t savgol_mcstream_latency(const SavgolMCStream *s);          /* == half_window */
+size_t savgol_mcstream_samples_received(const SavgolMCStream *s); /* per channel    */
+size_t savgol_mcstream_samples_output(const SavgolMCStream *s);   /* per channel    */
+/* Device pointer / element count of the carry state ([channels][2n] floats) for
+ * checkpointing. */
+float *savgol_mcstream_state(SavgolMCStream *s, size_t *n_floats);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SAVGOL_B200_H */

@@ -27,7 +27,7 @@
 
 #define SGO_MAX_N 32
 #define SGO_MAX_WS 65
-#define SGO_MAX_M 10
+#define SGO_MAX_M 64 /* the reference only requires m < 2n+1 and GenFact in range */
 #define SGO_MAX_D 4
 #define SGO_GF 76 /* ref: src/savgolFilter.c:110 (2*32 + 10 + 2) */
 
@@ -113,6 +113,7 @@ int sgo_config_ok(int n, int m, int d, float dt)
 {
     if (n < 1 || n > SGO_MAX_N) return -1;
     if (m >= 2 * n + 1) return -1;
+    if (2 * n + m + 1 >= SGO_GF) return -1; /* reference would index its table out of range */
     if (d > SGO_MAX_D) return -1;
     if (d > m) return -1;
     if (!(dt > 0.0f)) return -1;
@@ -124,7 +125,7 @@ int sgo_config_ok(int n, int m, int d, float dt)
  * ref: src/savgolFilter.c:368-409 */
 int sgo_weights_1d(int n, int m, int d, float *center, float *edge)
 {
-    if (n < 1 || n > SGO_MAX_N || m > SGO_MAX_M || m >= 2 * n + 1 || d > SGO_MAX_D || d > m)
+    if (n < 1 || n > SGO_MAX_N || m < 0 || m >= 2 * n + 1 || 2 * n + m + 1 >= SGO_GF || d > SGO_MAX_D || d > m)
         return -1;
     sgo_gf_build();
     const int ws = 2 * n + 1;

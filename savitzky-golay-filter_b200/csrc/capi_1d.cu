@@ -1,0 +1,355 @@
+// capi_1d.cu -- C ABI of the 1D batch path (include/savgol_b200.h part 1a + batch/halo extensions).
+// Mirrors the reference's argument checks, return codes and stderr messages
+// (src/savgolFilter.c:688-934); all arithmetic on signals happens in sg1d_kernel.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "coeffs.h"
+#include "engine.h"
+
+using sge::cuda_ok;
+using sge::MemKind;
+
+namespace {
+
+int arith_for_batch() { return sge::exact_mode() ? sg::ARITH_EXACT4 : sg::ARITH_FAST; }
+
+int mode_of(const SavgolFilter* f)
+{
+    switch (f->config.boundary) {
+        case SAVGOL_BOUNDARY_REFLECT: return sg::MODE_REFLECT;
+        case SAVGOL_BOUNDARY_PERIODIC: return sg::MODE_PERIODIC;
+        case SAVGOL_BOUNDARY_CONSTANT: return sg::MODE_CONSTANT;
+        default: return sg::MODE_POLY;
+    }
+}
+
+constexpr size_t kChunkFloats = size_t(16) << 20;  // 64 MiB of samples per staged chunk
+
+// Batch of contiguous-sample rows living in HOST memory (in and out both host).
+// Rows short enough are grouped into chunks of whole rows; a row longer than a chunk is cut
+// along its length and every piece carries explicit n-sample halos.
+bool run1d_host(const SavgolFilter* f, const float* in, float* out, size_t rows, size_t len,
+                size_t in_pitch, size_t out_pitch, int mode, bool poly_edges, int arith)
+{
+    std::lock_guard<std::mutex> lk(sge::g_pipe_mu);
+    const int n = f->config.half_window;
+    const size_t padl = static_cast<size_t>((n + 3) & ~3);
+    sge::Pipeline& P = sge::g_pipe;
+
+    if (len <= kChunkFloats) {
+        // ---- chunks of whole rows ----
+        const size_t rows_per = std::max<size_t>(1, std::min(rows, kChunkFloats / len));
+        if (!P.ensure(rows_per * len, rows_per * len)) return false;
+        size_t done = 0;
+        for (size_t c = 0; done < rows; ++c, done += rows_per) {
+            const int s = static_cast<int>(c % sge::Pipeline::kSlots);
+            const size_t nr = std::min(rows_per, rows - done);
+            if (c >= sge::Pipeline::kSlots) {
+                // slot reuse: its previous D2H must have drained before we overwrite d_out/d_in
+                if (!cuda_ok(cudaStreamWaitEvent(P.s_in, P.e_out[s], 0), "wait")) return false;
+            }
+            if (!cuda_ok(cudaMemcpy2DAsync(P.d_in[s], len * sizeof(float), in + done * in_pitch, in_pitch * sizeof(float),
+                                           len * sizeof(float), nr, cudaMemcpyHostToDevice, P.s_in), "H2D")) return false;
+            cudaEventRecord(P.e_in[s], P.s_in);
+            cudaStreamWaitEvent(P.s_k, P.e_in[s], 0);
+            if (c >= sge::Pipeline::kSlots) cudaStreamWaitEvent(P.s_k, P.e_out[s], 0);
+            sge::Problem1D p{};
+            p.filter = f; p.in = P.d_in[s]; p.out = P.d_out[s];
+            p.rows = nr; p.len = len;
+            p.in_row_bytes = p.out_row_bytes = len * sizeof(float);
+            p.in_stride = p.out_stride = 4;
+            p.mode = mode; p.edge_lead = p.edge_trail = poly_edges; p.arith = arith;
+            if (!sge::run1d_device(p, P.s_k)) return false;
+            cudaEventRecord(P.e_k[s], P.s_k);
+            cudaStreamWaitEvent(P.s_out, P.e_k[s], 0);
+            if (!cuda_ok(cudaMemcpy2DAsync(out + done * out_pitch, out_pitch * sizeof(float), P.d_out[s], len * sizeof(float),
+                                           len * sizeof(float), nr, cudaMemcpyDeviceToHost, P.s_out), "D2H")) return false;
+            cudaEventRecord(P.e_out[s], P.s_out);
+        }
+        return cuda_ok(cudaStreamSynchronize(P.s_out), "sync") && cuda_ok(cudaStreamSynchronize(P.s_k), "sync");
+    }
+
+    // ---- long rows: pieces of kChunkFloats samples with explicit halos ----
+    // slot layout: [padl-n slack | n left halo | piece | n right halo]
+    const size_t piece = kChunkFloats;
+    if (!P.ensure(padl + piece + 2 * sg::kMaxWs + n, piece + sg::kMaxWs)) return false;
+    size_t c = 0;
+    for (size_t r = 0; r < rows; ++r) {
+        const float* x = in + r * in_pitch;
+        float* y = out + r * out_pitch;
+        for (size_t s0 = 0; s0 < len; ++c) {
+            size_t s1 = std::min(len, s0 + piece);
+            if (len - s1 < static_cast<size_t>(2 * n + 1)) s1 = len;  // keep the last piece >= one window
+            const size_t plen = s1 - s0;
+            const int s = static_cast<int>(c % sge::Pipeline::kSlots);
+            if (c >= sge::Pipeline::kSlots && !cuda_ok(cudaStreamWaitEvent(P.s_in, P.e_out[s], 0), "wait")) return false;
+            float* base = P.d_in[s];
+            float* dx = base + padl;
+            const bool has_l = s0 > 0, has_r = s1 < len;
+            // body plus whatever neighbouring samples exist, in one copy
+            const size_t c0 = has_l ? s0 - n : s0, c1 = has_r ? s1 + n : s1;
+            if (!cuda_ok(cudaMemcpyAsync(dx - (s0 - c0), x + c0, (c1 - c0) * sizeof(float), cudaMemcpyHostToDevice, P.s_in), "H2D")) return false;
+            const float* lh = has_l ? dx - n : nullptr;
+            const float* rh = has_r ? dx + plen : nullptr;
+            if (mode == sg::MODE_PERIODIC && !(s0 == 0 && s1 == len)) {
+                // true ends of a periodic signal wrap around: fetch the far end as an explicit halo
+                if (!has_l) { cudaMemcpyAsync(dx - n, x + (len - n), n * sizeof(float), cudaMemcpyHostToDevice, P.s_in); lh = dx - n; }
+                if (!has_r) { cudaMemcpyAsync(dx + plen, x, n * sizeof(float), cudaMemcpyHostToDevice, P.s_in); rh = dx + plen; }
+            }
+            cudaEventRecord(P.e_in[s], P.s_in);
+            cudaStreamWaitEvent(P.s_k, P.e_in[s], 0);
+            if (c >= sge::Pipeline::kSlots) cudaStreamWaitEvent(P.s_k, P.e_out[s], 0);
+            sge::Problem1D p{};
+            p.filter = f; p.in = dx; p.out = P.d_out[s];
+            p.rows = 1; p.len = plen;
+            p.in_row_bytes = p.out_row_bytes = plen * sizeof(float);
+            p.in_stride = p.out_stride = 4;
+            p.lhalo = lh; p.rhalo = rh;
+            p.mode = mode;
+            p.edge_lead = poly_edges && !has_l; p.edge_trail = poly_edges && !has_r;
+            p.arith = arith;
+            if (!sge::run1d_device(p, P.s_k)) return false;
+            cudaEventRecord(P.e_k[s], P.s_k);
+            cudaStreamWaitEvent(P.s_out, P.e_k[s], 0);
+            if (!cuda_ok(cudaMemcpyAsync(y + s0, P.d_out[s], plen * sizeof(float), cudaMemcpyDeviceToHost, P.s_out), "D2H")) return false;
+            cudaEventRecord(P.e_out[s], P.s_out);
+            s0 = s1;
+        }
+    }
+    return cuda_ok(cudaStreamSynchronize(P.s_out), "sync") && cuda_ok(cudaStreamSynchronize(P.s_k), "sync");
+}
+
+// Dispatch on where the caller's buffers live.
+bool run1d_any(const SavgolFilter* f, const float* in, float* out, size_t rows, size_t len,
+               size_t in_pitch, size_t out_pitch, int mode, bool poly_edges)
+{
+    if (!sge::device_ready(true)) return false;
+    const MemKind ki = sge::classify(in), ko = sge::classify(out);
+    const int arith = arith_for_batch();
+    if (ki == MemKind::Device && ko == MemKind::Device) {
+        sge::Problem1D p{};
+        p.filter = f; p.in = in; p.out = out; p.rows = rows; p.len = len;
+        p.in_row_bytes = in_pitch * sizeof(float); p.out_row_bytes = out_pitch * sizeof(float);
+        p.in_stride = p.out_stride = 4;
+        p.mode = mode; p.edge_lead = p.edge_trail = poly_edges; p.arith = arith;
+        return sge::run1d_device(p, sge::current_stream());
+    }
+    if (ki != MemKind::Device && ko != MemKind::Device)
+        return run1d_host(f, in, out, rows, len, in_pitch, out_pitch, mode, poly_edges, arith);
+    fprintf(stderr, "savgol_b200: input and output must both be device pointers or both be host pointers\n");
+    return false;
+}
+
+}  // namespace
+
+// ============================================================================================
+extern "C" {
+
+SavgolFilter* savgol_create(const SavgolConfig* config)
+{
+    if (config == nullptr) return nullptr;  // ref: src/savgolFilter.c:641-643 (silent)
+    const char* why = nullptr;
+    if (!sgc::config1d_valid(config->half_window, config->poly_order, config->derivative, config->time_step, &why)) {
+        fprintf(stderr, "savgol: %s (half_window=%d poly_order=%d derivative=%d time_step=%f)\n", why,
+                config->half_window, config->poly_order, config->derivative, static_cast<double>(config->time_step));
+        return nullptr;
+    }
+    sge::FilterImpl* fi = static_cast<sge::FilterImpl*>(calloc(1, sizeof(sge::FilterImpl)));
+    if (!fi) {
+        fprintf(stderr, "savgol: failed to allocate filter context\n");
+        return nullptr;
+    }
+    fi->pub.config = *config;
+    fi->pub.window_size = 2 * config->half_window + 1;
+    fi->pub.dt_scale = sgc::dt_scale(config->time_step, config->derivative);
+    sgc::weights1d(config->half_window, config->poly_order, config->derivative, fi->pub.center_weights,
+                   &fi->pub.edge_weights[0][0]);
+    fi->magic = sge::kFilterMagic;
+    sge::register_filter(fi);
+    return &fi->pub;
+}
+
+void savgol_destroy(SavgolFilter* filter)
+{
+    if (!filter) return;
+    sge::FilterImpl* fi = sge::live_filter(filter);
+    if (fi) {
+        sge::unregister_filter(fi);
+        for (int d = 0; d < sge::kMaxDevices; ++d)
+            if (fi->edge_t[d]) {
+                int cur = 0;
+                cudaGetDevice(&cur);
+                cudaSetDevice(d);
+                cudaFree(fi->edge_t[d]);
+                cudaSetDevice(cur);
+            }
+        fi->magic = 0;
+    }
+    free(filter);
+}
+
+int savgol_apply_batch(const SavgolFilter* filter, const float* input, float* output,
+                       size_t n_signals, size_t length, size_t in_pitch, size_t out_pitch)
+{
+    if (filter == nullptr || input == nullptr || output == nullptr) {
+        fprintf(stderr, "savgol_apply: NULL pointer\n");
+        return -1;
+    }
+    if (length < static_cast<size_t>(filter->window_size)) {
+        fprintf(stderr, "savgol_apply: data length (%lu) < window size (%d)\n", static_cast<unsigned long>(length),
+                filter->window_size);
+        return -1;
+    }
+    if (n_signals == 0) return 0;
+    if (in_pitch < length || out_pitch < length) {
+        if (n_signals > 1) { fprintf(stderr, "savgol_apply_batch: pitch < length\n"); return -1; }
+        in_pitch = out_pitch = length;
+    }
+    const int mode = mode_of(filter);
+    return run1d_any(filter, input, output, n_signals, length, in_pitch, out_pitch, mode, mode == sg::MODE_POLY) ? 0 : -1;
+}
+
+int savgol_apply(const SavgolFilter* filter, const float* input, float* output, size_t length)
+{
+    return savgol_apply_batch(filter, input, output, 1, length, length, length);
+}
+
+size_t savgol_apply_valid(const SavgolFilter* filter, const float* input, size_t input_length, float* output)
+{
+    if (filter == nullptr || input == nullptr || output == nullptr) return 0;
+    if (input_length < static_cast<size_t>(filter->window_size)) return 0;
+    if (!sge::device_ready(true)) return 0;
+    const size_t n = filter->config.half_window;
+    const size_t out_len = input_length - 2 * n;
+    const MemKind ki = sge::classify(input), ko = sge::classify(output);
+    const int arith = arith_for_batch();
+    if (ki == MemKind::Device && ko == MemKind::Device) {
+        // VALID == the batch stencil on x+n with the first/last n samples as explicit halos
+        sge::Problem1D p{};
+        p.filter = filter; p.in = input + n; p.out = output; p.rows = 1; p.len = out_len;
+        p.in_row_bytes = p.out_row_bytes = out_len * sizeof(float);
+        p.in_stride = p.out_stride = 4;
+        p.lhalo = input; p.rhalo = input + (input_length - n);
+        p.mode = sg::MODE_POLY; p.arith = arith;
+        return sge::run1d_device(p, sge::current_stream()) ? out_len : 0;
+    }
+    if (ki == MemKind::Device || ko == MemKind::Device) {
+        fprintf(stderr, "savgol_b200: input and output must both be device pointers or both be host pointers\n");
+        return 0;
+    }
+    // host: stage the whole signal, run VALID on the device copy, bring L-2n samples back
+    cudaStream_t st = sge::current_stream();
+    float *din = nullptr, *dout = nullptr;
+    bool ok = cuda_ok(cudaMallocAsync(&din, input_length * sizeof(float), st), "cudaMallocAsync") &&
+              cuda_ok(cudaMallocAsync(&dout, out_len * sizeof(float), st), "cudaMallocAsync");
+    if (ok) ok = cuda_ok(cudaMemcpyAsync(din, input, input_length * sizeof(float), cudaMemcpyHostToDevice, st), "H2D");
+    if (ok) {
+        sge::Problem1D p{};
+        p.filter = filter; p.in = din + n; p.out = dout; p.rows = 1; p.len = out_len;
+        p.in_row_bytes = p.out_row_bytes = out_len * sizeof(float);
+        p.in_stride = p.out_stride = 4;
+        p.lhalo = din; p.rhalo = din + (input_length - n);
+        p.mode = sg::MODE_POLY; p.arith = arith;
+        ok = sge::run1d_device(p, st);
+    }
+    if (ok) ok = cuda_ok(cudaMemcpyAsync(output, dout, out_len * sizeof(float), cudaMemcpyDeviceToHost, st), "D2H");
+    if (ok) ok = cuda_ok(cudaStreamSynchronize(st), "sync");
+    if (din) cudaFreeAsync(din, st);
+    if (dout) cudaFreeAsync(dout, st);
+    return ok ? out_len : 0;
+}
+
+int savgol_apply_strided(const SavgolFilter* filter, const void* input, size_t in_stride, size_t in_offset,
+                         void* output, size_t out_stride, size_t out_offset, size_t count)
+{
+    if (filter == nullptr || input == nullptr || output == nullptr) return -1;  // ref: :882-884 (silent)
+    if (count < static_cast<size_t>(filter->window_size)) return -1;
+    if (!sge::device_ready(true)) return -1;
+    const MemKind ki = sge::classify(input), ko = sge::classify(output);
+    const int arith = arith_for_batch();
+    const char* ib = static_cast<const char*>(input) + in_offset;
+    char* ob = static_cast<char*>(output) + out_offset;
+    if (ki == MemKind::Device && ko == MemKind::Device) {
+        sge::Problem1D p{};
+        p.filter = filter; p.in = ib; p.out = ob; p.rows = 1; p.len = count;
+        p.in_row_bytes = count * in_stride; p.out_row_bytes = count * out_stride;
+        p.in_stride = in_stride; p.out_stride = out_stride;
+        p.mode = sg::MODE_POLY; p.edge_lead = p.edge_trail = true;  // strided ignores config.boundary (ref :911-928)
+        p.arith = arith;
+        return sge::run1d_device(p, sge::current_stream()) ? 0 : -1;
+    }
+    if (ki == MemKind::Device || ko == MemKind::Device) {
+        fprintf(stderr, "savgol_b200: input and output must both be device pointers or both be host pointers\n");
+        return -1;
+    }
+    // Host records: ship the input extent as raw bytes, gather on the device, return a contiguous
+    // result and scatter it on the host so that only the float fields the reference would write
+    // are touched.
+    cudaStream_t st = sge::current_stream();
+    const size_t in_bytes = (count - 1) * in_stride + sizeof(float);
+    char* din = nullptr;
+    float* dout = nullptr;
+    std::vector<float> tmp(count);
+    bool ok = cuda_ok(cudaMallocAsync(&din, in_bytes, st), "cudaMallocAsync") &&
+              cuda_ok(cudaMallocAsync(&dout, count * sizeof(float), st), "cudaMallocAsync");
+    if (ok) ok = cuda_ok(cudaMemcpyAsync(din, ib, in_bytes, cudaMemcpyHostToDevice, st), "H2D");
+    if (ok) {
+        sge::Problem1D p{};
+        p.filter = filter; p.in = din; p.out = dout; p.rows = 1; p.len = count;
+        p.in_row_bytes = in_bytes; p.out_row_bytes = count * sizeof(float);
+        p.in_stride = in_stride; p.out_stride = 4;
+        p.mode = sg::MODE_POLY; p.edge_lead = p.edge_trail = true; p.arith = arith;
+        ok = sge::run1d_device(p, st);
+    }
+    if (ok) ok = cuda_ok(cudaMemcpyAsync(tmp.data(), dout, count * sizeof(float), cudaMemcpyDeviceToHost, st), "D2H");
+    if (ok) ok = cuda_ok(cudaStreamSynchronize(st), "sync");
+    if (din) cudaFreeAsync(din, st);
+    if (dout) cudaFreeAsync(dout, st);
+    if (!ok) return -1;
+    for (size_t i = 0; i < count; ++i) *reinterpret_cast<float*>(ob + i * out_stride) = tmp[i];
+    return 0;
+}
+
+int savgol_apply_halo(const SavgolFilter* filter, const float* input, float* output, size_t length,
+                      const float* left_halo, const float* right_halo)
+{
+    if (filter == nullptr || input == nullptr || output == nullptr) {
+        fprintf(stderr, "savgol_apply_halo: NULL pointer\n");
+        return -1;
+    }
+    if (length < static_cast<size_t>(filter->window_size)) {
+        fprintf(stderr, "savgol_apply_halo: slice length (%lu) < window size (%d)\n", static_cast<unsigned long>(length),
+                filter->window_size);
+        return -1;
+    }
+    const int mode = mode_of(filter);
+    if (mode == sg::MODE_PERIODIC && ((left_halo == nullptr) != (right_halo == nullptr))) {
+        fprintf(stderr, "savgol_apply_halo: a periodic slice needs both halos (or none)\n");
+        return -1;
+    }
+    if (!sge::device_ready(true)) return -1;
+    if (sge::classify(input) != MemKind::Device || sge::classify(output) != MemKind::Device ||
+        (left_halo && sge::classify(left_halo) != MemKind::Device) ||
+        (right_halo && sge::classify(right_halo) != MemKind::Device)) {
+        fprintf(stderr, "savgol_apply_halo: slices and halos must be device pointers\n");
+        return -1;
+    }
+    sge::Problem1D p{};
+    p.filter = filter; p.in = input; p.out = output; p.rows = 1; p.len = length;
+    p.in_row_bytes = p.out_row_bytes = length * sizeof(float);
+    p.in_stride = p.out_stride = 4;
+    p.lhalo = left_halo; p.rhalo = right_halo;
+    p.mode = mode;
+    p.edge_lead = mode == sg::MODE_POLY && left_halo == nullptr;
+    p.edge_trail = mode == sg::MODE_POLY && right_halo == nullptr;
+    p.arith = arith_for_batch();
+    return sge::run1d_device(p, sge::current_stream()) ? 0 : -1;
+}
+
+}  // extern "C"

@@ -1,0 +1,364 @@
+// capi_2d.cu -- C ABI of the 2D filter (include/savgol_b200.h part 1c + batch extension).
+// Argument checks / return codes follow src/savgol2d.c:271-618.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <unordered_set>
+#include <vector>
+
+#include "coeffs.h"
+#include "engine.h"
+#include "sg2d.h"
+
+using sge::cuda_ok;
+using sge::MemKind;
+
+namespace {
+
+struct Filter2DImpl {
+    Savgol2DFilter pub;  // public ABI prefix (ref: include/iterative/savgol2d.h:95-103)
+    uint64_t magic;
+    float* d_weights[sge::kMaxDevices];
+    sg2d::SepPlan plan;  // separable factorisation of the weight surface (sg2d_sep.cu)
+};
+constexpr uint64_t kMagic2D = 0x5347423230303244ULL;
+
+std::mutex g_mu2d;
+std::unordered_set<const void*> g_live2d;
+
+Filter2DImpl* live2d(const Savgol2DFilter* f)
+{
+    std::lock_guard<std::mutex> lk(g_mu2d);
+    if (!g_live2d.count(f)) return nullptr;
+    Filter2DImpl* fi = reinterpret_cast<Filter2DImpl*>(const_cast<Savgol2DFilter*>(f));
+    return fi->magic == kMagic2D ? fi : nullptr;
+}
+
+// device copy of the weights on the current device (*temp set when it is a per-call upload)
+const float* weights_device(const Savgol2DFilter* f, cudaStream_t st, float** temp)
+{
+    *temp = nullptr;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    Filter2DImpl* fi = live2d(f);
+    const size_t bytes = static_cast<size_t>(f->window_area) * sizeof(float);
+    if (fi && dev < sge::kMaxDevices) {
+        std::lock_guard<std::mutex> lk(g_mu2d);
+        if (!fi->d_weights[dev]) {
+            float* d = nullptr;
+            if (!cuda_ok(cudaMalloc(&d, bytes), "cudaMalloc(2d weights)")) return nullptr;
+            if (!cuda_ok(cudaMemcpy(d, f->weights, bytes, cudaMemcpyHostToDevice), "upload 2d weights")) { cudaFree(d); return nullptr; }
+            fi->d_weights[dev] = d;
+        }
+        return fi->d_weights[dev];
+    }
+    float* d = nullptr;
+    if (!cuda_ok(cudaMallocAsync(&d, bytes, st), "cudaMallocAsync(2d weights)")) return nullptr;
+    if (!cuda_ok(cudaMemcpyAsync(d, f->weights, bytes, cudaMemcpyHostToDevice, st), "upload 2d weights")) { cudaFreeAsync(d, st); return nullptr; }
+    *temp = d;
+    return d;
+}
+
+// One launch over device-resident images.
+bool run2d_device(const Savgol2DFilter* f, const float* in, int rows, int cols, long long is, long long ipitch,
+                  float* out, long long os, long long opitch, long long n_images, int boundary, cudaStream_t st)
+{
+    const int nx = f->config.half_window_x, ny = f->config.half_window_y;
+    sg2d::Args2D a{};
+    a.in = in; a.out = out;
+    a.rows = rows; a.cols = cols;
+    a.nx = nx; a.ny = ny;
+    a.in_stride = is; a.out_stride = os;
+    a.in_image_pitch = ipitch; a.out_image_pitch = opitch;
+    a.n_images = n_images;
+    a.boundary = boundary;
+    a.scale = f->scale;
+    if (boundary == sg2d::B_VALID) {
+        a.out_rows = rows - 2 * ny; a.out_cols = cols - 2 * nx;
+        a.cy = ny; a.cx = nx;
+    } else {
+        a.out_rows = rows; a.out_cols = cols;
+        a.cy = a.cx = 0;
+    }
+    const bool exact = sge::exact_mode() != 0;
+    Filter2DImpl* fi = live2d(f);
+    if (!exact && fi && fi->plan.rank > 0) {
+        // in-place is not supported by the tiled kernels; go through scratch like the 1D path
+        return cuda_ok(sg2d::launch_separable(a, fi->plan, st), "sg2d separable launch");
+    }
+    float* temp = nullptr;
+    a.weights = weights_device(f, st, &temp);
+    if (!a.weights) return false;
+    const bool ok = cuda_ok(sg2d::launch_direct(a, exact, st), "sg2d direct launch");
+    if (temp) cudaFreeAsync(temp, st);
+    return ok;
+}
+
+bool ranges_overlap2d(const float* a, size_t an, const float* b, size_t bn) { return a < b + bn && b < a + an; }
+
+// Images anywhere (host or device).  `valid_origin`: VALID writes its first output at out[0]
+// (savgol2d_apply_valid) instead of out[ny*os+nx] (savgol2d_apply with BOUNDARY_VALID).
+int apply2d_any(const Savgol2DFilter* f, const float* in, int rows, int cols, int is, size_t ipitch,
+                float* out, int os, size_t opitch, size_t n_images, int boundary)
+{
+    if (!sge::device_ready(true)) return -1;
+    const int nx = f->config.half_window_x, ny = f->config.half_window_y;
+    const int orows = boundary == sg2d::B_VALID ? rows - 2 * ny : rows;
+    const int ocols = boundary == sg2d::B_VALID ? cols - 2 * nx : cols;
+    const MemKind ki = sge::classify(in), ko = sge::classify(out);
+    cudaStream_t st = sge::current_stream();
+    if (ki == MemKind::Device && ko == MemKind::Device) {
+        const size_t in_span = (n_images - 1) * ipitch + static_cast<size_t>(rows - 1) * is + cols;
+        const size_t out_span = (n_images - 1) * opitch + static_cast<size_t>(orows - 1) * os + ocols;
+        if (ranges_overlap2d(in, in_span, out, out_span)) {
+            // aliased: compute into scratch, copy back (out-of-place result, like the 1D path)
+            float* scratch = nullptr;
+            const size_t img = static_cast<size_t>(orows) * ocols;
+            if (!cuda_ok(cudaMallocAsync(&scratch, n_images * img * sizeof(float), st), "cudaMallocAsync(2d in-place)")) return -1;
+            bool ok = run2d_device(f, in, rows, cols, is, static_cast<long long>(ipitch), scratch, ocols,
+                                   static_cast<long long>(img), static_cast<long long>(n_images), boundary, st);
+            for (size_t i = 0; ok && i < n_images; ++i)
+                ok = cuda_ok(cudaMemcpy2DAsync(out + i * opitch, static_cast<size_t>(os) * sizeof(float), scratch + i * img,
+                                               static_cast<size_t>(ocols) * sizeof(float), static_cast<size_t>(ocols) * sizeof(float),
+                                               orows, cudaMemcpyDeviceToDevice, st), "2d copy back");
+            cudaFreeAsync(scratch, st);
+            return ok ? 0 : -1;
+        }
+        return run2d_device(f, in, rows, cols, is, static_cast<long long>(ipitch), out, os, static_cast<long long>(opitch),
+                            static_cast<long long>(n_images), boundary, st) ? 0 : -1;
+    }
+    if (ki == MemKind::Device || ko == MemKind::Device) {
+        fprintf(stderr, "savgol_b200: input and output must both be device pointers or both be host pointers\n");
+        return -1;
+    }
+    // host images: one image per pipeline slot, H2D / kernel / D2H overlapped across images
+    std::lock_guard<std::mutex> lk(sge::g_pipe_mu);
+    sge::Pipeline& P = sge::g_pipe;
+    const size_t img_in = static_cast<size_t>(rows) * cols, img_out = static_cast<size_t>(orows) * ocols;
+    if (!P.ensure(img_in, img_out)) return -1;
+    for (size_t i = 0; i < n_images; ++i) {
+        const int s = static_cast<int>(i % sge::Pipeline::kSlots);
+        if (i >= sge::Pipeline::kSlots) cudaStreamWaitEvent(P.s_in, P.e_out[s], 0);
+        if (!cuda_ok(cudaMemcpy2DAsync(P.d_in[s], static_cast<size_t>(cols) * sizeof(float), in + i * ipitch,
+                                       static_cast<size_t>(is) * sizeof(float), static_cast<size_t>(cols) * sizeof(float), rows,
+                                       cudaMemcpyHostToDevice, P.s_in), "H2D")) return -1;
+        cudaEventRecord(P.e_in[s], P.s_in);
+        cudaStreamWaitEvent(P.s_k, P.e_in[s], 0);
+        if (i >= sge::Pipeline::kSlots) cudaStreamWaitEvent(P.s_k, P.e_out[s], 0);
+        if (!run2d_device(f, P.d_in[s], rows, cols, cols, 0, P.d_out[s], ocols, 0, 1, boundary, P.s_k)) return -1;
+        cudaEventRecord(P.e_k[s], P.s_k);
+        cudaStreamWaitEvent(P.s_out, P.e_k[s], 0);
+        if (!cuda_ok(cudaMemcpy2DAsync(out + i * opitch, static_cast<size_t>(os) * sizeof(float), P.d_out[s],
+                                       static_cast<size_t>(ocols) * sizeof(float), static_cast<size_t>(ocols) * sizeof(float), orows,
+                                       cudaMemcpyDeviceToHost, P.s_out), "D2H")) return -1;
+        cudaEventRecord(P.e_out[s], P.s_out);
+    }
+    return cuda_ok(cudaStreamSynchronize(P.s_out), "sync") && cuda_ok(cudaStreamSynchronize(P.s_k), "sync") ? 0 : -1;
+}
+
+}  // namespace
+
+extern "C" {
+
+bool savgol2d_config_valid(const Savgol2DConfig* c)
+{
+    if (!c) return false;
+    return sgc::config2d_valid(c->half_window_x, c->half_window_y, c->poly_order, c->deriv_x, c->deriv_y, c->delta_x, c->delta_y);
+}
+
+Savgol2DFilter* savgol2d_create(const Savgol2DConfig* config)
+{
+    if (!savgol2d_config_valid(config)) {
+        fprintf(stderr, "savgol2d_create: invalid configuration\n");
+        return nullptr;
+    }
+    Filter2DImpl* fi = static_cast<Filter2DImpl*>(calloc(1, sizeof(Filter2DImpl)));
+    if (!fi) return nullptr;
+    Savgol2DFilter* f = &fi->pub;
+    f->config = *config;
+    f->window_width = 2 * config->half_window_x + 1;
+    f->window_height = 2 * config->half_window_y + 1;
+    f->window_area = f->window_width * f->window_height;
+    f->num_terms = savgol2d_num_terms(config->poly_order);
+    f->scale = sgc::scale2d(config->deriv_x, config->deriv_y, config->delta_x, config->delta_y);
+    f->weights = static_cast<float*>(malloc(static_cast<size_t>(f->window_area) * sizeof(float)));
+    if (!f->weights) { free(fi); return nullptr; }
+    double coef[28];
+    if (!sgc::weights2d(config->half_window_x, config->half_window_y, config->poly_order, config->deriv_x, config->deriv_y,
+                        f->weights, coef)) {
+        fprintf(stderr, "savgol2d_create: weight computation failed\n");
+        free(f->weights);
+        free(fi);
+        return nullptr;
+    }
+    sg2d::plan_separable(config->half_window_x, config->half_window_y, config->poly_order, coef, f->weights, &fi->plan);
+    fi->magic = kMagic2D;
+    {
+        std::lock_guard<std::mutex> lk(g_mu2d);
+        g_live2d.insert(fi);
+    }
+    return f;
+}
+
+void savgol2d_destroy(Savgol2DFilter* filter)
+{
+    if (!filter) return;
+    Filter2DImpl* fi = live2d(filter);
+    if (fi) {
+        {
+            std::lock_guard<std::mutex> lk(g_mu2d);
+            g_live2d.erase(fi);
+        }
+        for (int d = 0; d < sge::kMaxDevices; ++d)
+            if (fi->d_weights[d]) {
+                int cur = 0;
+                cudaGetDevice(&cur);
+                cudaSetDevice(d);
+                cudaFree(fi->d_weights[d]);
+                cudaSetDevice(cur);
+            }
+        fi->magic = 0;
+    }
+    free(filter->weights);
+    free(filter);
+}
+
+int savgol2d_apply_batch(const Savgol2DFilter* filter, const float* input, int rows, int cols, int in_stride,
+                         size_t in_image_pitch, float* output, int out_stride, size_t out_image_pitch, size_t n_images,
+                         Savgol2DBoundary boundary)
+{
+    if (!filter || !input || !output) return -1;
+    if (n_images == 0) return 0;
+    const int nx = filter->config.half_window_x, ny = filter->config.half_window_y;
+    if (rows <= 0 || cols <= 0) return -1;
+    if (boundary == SAVGOL2D_BOUNDARY_VALID) {
+        if (rows - 2 * ny <= 0 || cols - 2 * nx <= 0) return -1;  // ref: src/savgol2d.c:371
+        // the reference writes the valid block at offset (ny, nx) of `output`; border untouched
+        return apply2d_any(filter, input, rows, cols, in_stride, in_image_pitch,
+                           output + static_cast<ptrdiff_t>(ny) * out_stride + nx, out_stride, out_image_pitch, n_images,
+                           sg2d::B_VALID);
+    }
+    const int b = boundary == SAVGOL2D_BOUNDARY_REFLECT ? sg2d::B_REFLECT : sg2d::B_CONSTANT;  // ref: :428-445 (else = clamp)
+    return apply2d_any(filter, input, rows, cols, in_stride, in_image_pitch, output, out_stride, out_image_pitch, n_images, b);
+}
+
+int savgol2d_apply(const Savgol2DFilter* filter, const float* input, int rows, int cols, int in_stride,
+                   float* output, int out_stride, Savgol2DBoundary boundary)
+{
+    return savgol2d_apply_batch(filter, input, rows, cols, in_stride, 0, output, out_stride, 0, 1, boundary);
+}
+
+int savgol2d_apply_valid(const Savgol2DFilter* filter, const float* input, int rows, int cols, int in_stride,
+                         float* output, int out_stride)
+{
+    if (!filter || !input || !output) return -1;
+    const int nx = filter->config.half_window_x, ny = filter->config.half_window_y;
+    if (rows - 2 * ny <= 0 || cols - 2 * nx <= 0) return -1;
+    return apply2d_any(filter, input, rows, cols, in_stride, 0, output, out_stride, 0, 1, sg2d::B_VALID);
+}
+
+// Convenience wrappers: one filter per requested component, as the reference composes them
+// (src/savgol2d.c:462-618).
+static int component(int hx, int hy, int order, int dx, int dy, const float* in, int rows, int cols, int stride, float* out,
+                     float delta_x, float delta_y, Savgol2DBoundary boundary)
+{
+    Savgol2DConfig cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.half_window_x = static_cast<uint8_t>(hx);
+    cfg.half_window_y = static_cast<uint8_t>(hy);
+    cfg.poly_order = static_cast<uint8_t>(order);
+    cfg.deriv_x = static_cast<uint8_t>(dx);
+    cfg.deriv_y = static_cast<uint8_t>(dy);
+    cfg.delta_x = delta_x;
+    cfg.delta_y = delta_y;
+    Savgol2DFilter* f = savgol2d_create(&cfg);
+    if (!f) return -1;
+    const int rc = savgol2d_apply(f, in, rows, cols, stride, out, stride, boundary);
+    savgol2d_destroy(f);
+    return rc;
+}
+
+int savgol2d_gradient(int hx, int hy, int order, const float* input, int rows, int cols, int stride,
+                      float* grad_x, float* grad_y, float delta_x, float delta_y, Savgol2DBoundary boundary)
+{
+    if (grad_x) {
+        const int rc = component(hx, hy, order, 1, 0, input, rows, cols, stride, grad_x, delta_x, delta_y, boundary);
+        if (rc != 0) return rc;
+    }
+    if (grad_y) {
+        const int rc = component(hx, hy, order, 0, 1, input, rows, cols, stride, grad_y, delta_x, delta_y, boundary);
+        if (rc != 0) return rc;
+    }
+    return 0;
+}
+
+int savgol2d_hessian(int hx, int hy, int order, const float* input, int rows, int cols, int stride,
+                     float* hess_xx, float* hess_xy, float* hess_yy, float delta_x, float delta_y, Savgol2DBoundary boundary)
+{
+    if (order < 2) {
+        fprintf(stderr, "savgol2d_hessian: poly_order must be >= 2\n");
+        return -1;
+    }
+    if (hess_xx) {
+        const int rc = component(hx, hy, order, 2, 0, input, rows, cols, stride, hess_xx, delta_x, delta_y, boundary);
+        if (rc != 0) return rc;
+    }
+    if (hess_xy) {
+        const int rc = component(hx, hy, order, 1, 1, input, rows, cols, stride, hess_xy, delta_x, delta_y, boundary);
+        if (rc != 0) return rc;
+    }
+    if (hess_yy) {
+        const int rc = component(hx, hy, order, 0, 2, input, rows, cols, stride, hess_yy, delta_x, delta_y, boundary);
+        if (rc != 0) return rc;
+    }
+    return 0;
+}
+
+__global__ void add_rows_kernel(float* __restrict__ dst, const float* __restrict__ src, int rows, int cols, long long stride)
+{
+    const long long total = static_cast<long long>(rows) * cols;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / cols, c = i - r * cols;
+        dst[r * stride + c] = __fadd_rn(dst[r * stride + c], src[r * stride + c]);
+    }
+}
+
+int savgol2d_laplacian(int hx, int hy, int order, const float* input, int rows, int cols, int stride, float* output,
+                       float delta_x, float delta_y, Savgol2DBoundary boundary)
+{
+    if (order < 2) {
+        fprintf(stderr, "savgol2d_laplacian: poly_order must be >= 2\n");
+        return -1;
+    }
+    if (!input || !output) return -1;
+    int rc = component(hx, hy, order, 2, 0, input, rows, cols, stride, output, delta_x, delta_y, boundary);
+    if (rc != 0) return rc;
+    const size_t span = static_cast<size_t>(rows) * stride;
+    if (sge::classify(output) == MemKind::Device) {
+        cudaStream_t st = sge::current_stream();
+        float* tmp = nullptr;
+        if (!cuda_ok(cudaMallocAsync(&tmp, span * sizeof(float), st), "cudaMallocAsync(laplacian)")) return -1;
+        cudaMemsetAsync(tmp, 0, span * sizeof(float), st);
+        rc = component(hx, hy, order, 0, 2, input, rows, cols, stride, tmp, delta_x, delta_y, boundary);
+        if (rc == 0) {
+            // output += tmp over the rows x cols region only (ref: src/savgol2d.c:607-614)
+            const long long total = static_cast<long long>(rows) * cols;
+            const unsigned grid = static_cast<unsigned>(std::min<long long>((total + 255) / 256, 148 * 16));
+            add_rows_kernel<<<grid, 256, 0, st>>>(output, tmp, rows, cols, stride);
+            if (!cuda_ok(cudaGetLastError(), "laplacian add")) rc = -1;
+        }
+        cudaFreeAsync(tmp, st);
+        return rc;
+    }
+    std::vector<float> tmp(span, 0.0f);
+    rc = component(hx, hy, order, 0, 2, input, rows, cols, stride, tmp.data(), delta_x, delta_y, boundary);
+    if (rc == 0)
+        for (int y = 0; y < rows; ++y)
+            for (int x = 0; x < cols; ++x) output[static_cast<size_t>(y) * stride + x] += tmp[static_cast<size_t>(y) * stride + x];
+    return rc;
+}
+
+}  // extern "C"

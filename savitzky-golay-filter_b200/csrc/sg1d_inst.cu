@@ -1,0 +1,25 @@
+// sg1d_inst.cu -- explicit instantiations of sg1d_kernel for four half-windows.
+// Compiled eight times (-DSG_GROUP=0..7) so the 160 fully unrolled kernels build in parallel.
+#include "sg1d_kernel.cuh"
+#include "sg1d_launch.h"
+
+#ifndef SG_GROUP
+#error "compile with -DSG_GROUP=<0..7>"
+#endif
+
+namespace sg {
+
+#define SG_ROW(N)                                                                                   \
+    {&sg1d_kernel<N, false, ARITH_FAST>}, {&sg1d_kernel<N, false, ARITH_EXACT4>},                   \
+    {&sg1d_kernel<N, false, ARITH_EXACTSEQ>}, {&sg1d_kernel<N, true, ARITH_FAST>},                  \
+    {&sg1d_kernel<N, true, ARITH_EXACTSEQ>}
+
+#define SG_CAT_(a, b) a##b
+#define SG_CAT(a, b) SG_CAT_(a, b)
+
+static const Kernel1D SG_CAT(kTable, SG_GROUP)[4 * V_COUNT] = {
+    SG_ROW(4 * SG_GROUP + 1), SG_ROW(4 * SG_GROUP + 2), SG_ROW(4 * SG_GROUP + 3), SG_ROW(4 * SG_GROUP + 4)};
+
+const Kernel1D* SG_CAT(sg1d_group_table_, SG_GROUP)() { return SG_CAT(kTable, SG_GROUP); }
+
+}  // namespace sg

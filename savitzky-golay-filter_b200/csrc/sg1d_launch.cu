@@ -1,0 +1,74 @@
+// sg1d_launch.cu -- grid sizing and dispatch for the 1D kernels.
+#include "sg1d_launch.h"
+
+#include <atomic>
+#include <mutex>
+
+namespace sg {
+
+#define SG_DECL(g) const Kernel1D* sg1d_group_table_##g();
+SG_DECL(0) SG_DECL(1) SG_DECL(2) SG_DECL(3) SG_DECL(4) SG_DECL(5) SG_DECL(6) SG_DECL(7)
+#undef SG_DECL
+
+std::atomic<unsigned long long> g_launches{0};
+
+const Kernel1D* sg1d_group_table(int group)
+{
+    switch (group) {
+        case 0: return sg1d_group_table_0();
+        case 1: return sg1d_group_table_1();
+        case 2: return sg1d_group_table_2();
+        case 3: return sg1d_group_table_3();
+        case 4: return sg1d_group_table_4();
+        case 5: return sg1d_group_table_5();
+        case 6: return sg1d_group_table_6();
+        case 7: return sg1d_group_table_7();
+        default: return nullptr;
+    }
+}
+
+namespace {
+struct GridInfo { int blocks_per_sm = 0; };
+GridInfo g_grid[kMaxN + 1][V_COUNT];  // per (n, variant); filled lazily (same value on every B200)
+int g_sms[64];
+std::mutex g_mu;
+}  // namespace
+
+cudaError_t sg1d_launch(int n, int variant, const W1D& w, Args1D& a, cudaStream_t stream)
+{
+    if (n < 1 || n > kMaxN || variant < 0 || variant >= V_COUNT) return cudaErrorInvalidValue;
+    const Kernel1D& k = sg1d_group_table((n - 1) / 4)[((n - 1) % 4) * V_COUNT + variant];
+
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    int bps, sms;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        GridInfo& gi = g_grid[n][variant];
+        if (gi.blocks_per_sm == 0) {
+            int nb = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k.kernel, kThreads, 0);
+            if (e != cudaSuccess) return e;
+            gi.blocks_per_sm = nb > 0 ? nb : 1;
+        }
+        if (dev < 64 && g_sms[dev] == 0) {
+            e = cudaDeviceGetAttribute(&g_sms[dev], cudaDevAttrMultiProcessorCount, dev);
+            if (e != cudaSuccess) return e;
+        }
+        bps = gi.blocks_per_sm;
+        sms = dev < 64 ? g_sms[dev] : 148;
+    }
+
+    a.tiles_per_row = (a.len + kTile - 1) / kTile;
+    a.ntiles = a.tiles_per_row * a.rows;
+    if (a.ntiles <= 0) return cudaSuccess;
+    // persistent CTAs: one per resident slot (148 SMs x blocks/SM on a B200), round-robin over tiles
+    long long grid = static_cast<long long>(sms) * bps;
+    if (grid > a.ntiles) grid = a.ntiles;
+    k.kernel<<<static_cast<unsigned>(grid), kThreads, 0, stream>>>(w, a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+}  // namespace sg

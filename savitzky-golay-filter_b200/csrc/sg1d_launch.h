@@ -1,0 +1,21 @@
+// sg1d_launch.h -- host-side dispatch table of the 1D kernel instantiations.
+#pragma once
+#include "sg_common.cuh"
+
+namespace sg {
+
+// Variant index inside a half-window's row of the table.
+enum : int { V_BATCH_FAST = 0, V_BATCH_EXACT4 = 1, V_BATCH_EXACTSEQ = 2, V_STREAM_FAST = 3, V_STREAM_EXACTSEQ = 4, V_COUNT = 5 };
+
+struct Kernel1D {
+    void (*kernel)(const W1D, const Args1D);  // __global__ entry
+};
+
+// Defined once per instantiation group (sg1d_inst.cu compiled with -DSG_GROUP=g covers
+// half-windows 4g+1 .. 4g+4).
+const Kernel1D* sg1d_group_table(int group);
+
+// Grid sizing + launch.  Returns cudaSuccess or the launch error.
+cudaError_t sg1d_launch(int n, int variant, const W1D& w, Args1D& args, cudaStream_t stream);
+
+}  // namespace sg

@@ -1,0 +1,45 @@
+// sg2d.h -- launch descriptors of the 2D kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sg2d {
+
+// ref: include/iterative/savgol2d.h:108-112
+enum : int { B_VALID = 0, B_CONSTANT = 1, B_REFLECT = 2 };
+
+// out[img][oy][ox] = scale * sum_{wy,wx} W[wy][wx] * in[img][map(oy+cy-ny+wy)][map(ox+cx-nx+wx)]
+// for oy < out_rows, ox < out_cols.  Full-size modes: cy = cx = 0, out = rows x cols, map = clamp /
+// reflect.  VALID: cy = ny, cx = nx, out = (rows-2ny) x (cols-2nx), map is the identity.
+struct Args2D {
+    const float* in;
+    float* out;
+    const float* weights;   // device, [2ny+1][2nx+1]
+    int rows, cols;         // input image size
+    int out_rows, out_cols;
+    int cy, cx;
+    int nx, ny;
+    long long in_stride, out_stride;            // elements between rows
+    long long in_image_pitch, out_image_pitch;  // elements between images
+    long long n_images;
+    int boundary;
+    float scale;
+};
+
+cudaError_t launch_direct(const Args2D& a, bool exact, cudaStream_t stream);
+
+// Separable representation of the weight surface: W[y][x] = sum_r col[r][y] * row[r][x], r < rank
+// (exact up to fp32 rounding of the factors, because W is a polynomial of total degree <= 6 in
+// (x,y); see sg2d_sep.cu).  rank == 0 means "no usable factorisation, use the direct kernel".
+constexpr int kMaxRank = 4;
+struct SepPlan {
+    int rank;
+    int nx, ny;
+    float row[kMaxRank][33];  // row[r][x + nx]
+    float col[kMaxRank][33];  // col[r][y + ny]
+    float max_err;            // max |W - sum_r col*row| / max|W|
+};
+void plan_separable(int nx, int ny, int order, const double* coef, const float* weights, SepPlan* plan);
+cudaError_t launch_separable(const Args2D& a, const SepPlan& plan, cudaStream_t stream);
+
+}  // namespace sg2d

@@ -1,0 +1,78 @@
+// sg_common.cuh -- shared device helpers and the host-visible launch descriptors of the
+// sm_100a Savitzky-Golay kernels.  Nothing here is a port of reference code: the reference is
+// scalar C (src/savgolFilter.c), this is the B200 execution plan for the same arithmetic.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sg {
+
+constexpr int kThreads = 128;              // 4 warps per CTA
+constexpr int kR = 32;                     // consecutive outputs per thread (register sliding window)
+constexpr int kTile = kThreads * kR;       // 4096 outputs per tile
+constexpr int kMaxN = 32;
+constexpr int kMaxWs = 2 * kMaxN + 1;      // 65, ref: include/iterative/savgolFilter.h:42
+
+// Boundary synthesis of the virtual pad samples (ref: src/savgolFilter.c:442-482).
+enum : int { MODE_POLY = 0, MODE_REFLECT = 1, MODE_PERIODIC = 2, MODE_CONSTANT = 3 };
+// Arithmetic flavour.  FAST: packed-FMA chains (within 1e-6*max|x|/dt^d of the reference).
+// EXACT4: the reference's 4-chain order with unfused multiply/add (src/savgolFilter.c:547-580)
+//         -> bit-identical to savgol_apply.
+// EXACTSEQ: single sequential accumulator, unfused (src/savgol_stream.c:25-38) -> bit-identical
+//         to the stream API.
+enum : int { ARITH_FAST = 0, ARITH_EXACT4 = 1, ARITH_EXACTSEQ = 2 };
+
+// Centre weights travel as a kernel parameter: they land in constant bank 0 and ptxas keeps
+// them in uniform registers, so every FFMA2 takes its weight as a UR operand.
+struct W1D { float w[kMaxWs]; };
+
+// One launch = `rows` independent signals of `len` samples, cut into tiles of kTile outputs.
+// Virtual signal V per row:  V = [ lead pad | x[0..len) | n pad ],  out[o] = scale * sum_k w[k] V[o+k],
+// lead = n (batch: output o is centred on x[o]) or 2n (stream: output o is centred on x[o-n],
+// the pad is the carried history).
+struct Args1D {
+    const char* in;          // sample i of row r at in + r*in_row_bytes + i*in_stride
+    char* out;               // same addressing for outputs
+    long long rows, len;
+    long long out_len;       // outputs [0,out_len) of every row are stored (out_len <= len)
+    long long in_row_bytes, out_row_bytes;
+    long long in_stride, out_stride;   // bytes between consecutive samples (4 = contiguous)
+    const float* lhalo;      // optional explicit left pad: `lead` samples per row, chronological
+    const float* rhalo;      // optional explicit right pad: n samples per row
+    long long lhalo_pitch, rhalo_pitch;  // elements between rows
+    const float* edge_t;     // polynomial edge table, transposed: edge_t[k*32 + e] = E[e][k]
+    float* state_out;        // stream: receives the last state_w samples of [lead pad | x] per row
+    long long state_pitch;
+    int state_w;
+    float scale;             // 1/dt^d, applied as a separate multiply like the reference
+    int mode;                // MODE_* used where a halo pointer is null
+    int edge_lead, edge_trail;  // 1: outputs [0,n) / [len-n,len) come from the polynomial edge table
+    long long tiles_per_row, ntiles;
+};
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
+{
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
+{
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(kPending) : "memory");
+}
+
+// Streaming store: outputs are written once and never re-read by this kernel.
+__device__ __forceinline__ void st_cs_f4(float* p, float4 v)
+{
+    asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+}  // namespace sg

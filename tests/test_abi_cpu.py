@@ -1,0 +1,147 @@
+"""CPU-side checks of the drop-in boundary (no GPU, no compute launches):
+the C-ABI library loads, exports every symbol include/savgol_b200.h declares, keeps the
+reference's struct layouts, builds weight tables bit-identical to the oracle's, and runs the
+host-only parts of the API (creation/validation, the scalar stream shim) like the reference."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import savgol_b200 as sg
+from savgol_b200 import _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "savgol_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(savgol[A-Za-z0-9_]*)\s*\(", hdr))
+    declared -= {"savgol2d_valid_size", "savgol2d_num_terms"}  # static inline in the header
+    lib = sg.lib()
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, missing
+    assert declared == set(_capi.PROTOTYPES), declared ^ set(_capi.PROTOTYPES)
+    assert lib.savgol_b200_version() == 100
+
+
+def test_struct_layouts_match_reference_abi():
+    # SURVEY.md section 0 (probed from the reference headers with gcc)
+    assert C.sizeof(_capi.SavgolConfig) == 12
+    assert C.sizeof(_capi.SavgolFilterStruct) == 8600
+    assert _capi.SavgolFilterStruct.window_size.offset == 12
+    assert _capi.SavgolFilterStruct.dt_scale.offset == 16
+    assert _capi.SavgolFilterStruct.center_weights.offset == 20
+    assert _capi.SavgolFilterStruct.edge_weights.offset == 280
+    assert C.sizeof(_capi.SavgolStreamStruct) == 296
+    assert C.sizeof(_capi.Savgol2DConfig) == 16
+    assert C.sizeof(_capi.Savgol2DFilterStruct) == 48
+
+
+def test_compat_headers_compile_reference_style_code(tmp_path):
+    # a translation unit written against the reference's header names must compile against ours
+    src = tmp_path / "t.c"
+    src.write_text('#include "savgolFilter.h"\n#include "savgol_stream.h"\n#include "savgol2d.h"\n'
+                   "int main(void){ SavgolConfig c = SAVGOL_DERIV1(5,2,0.5f); SavgolStream s; Savgol2DConfig d;"
+                   "(void)c;(void)s;(void)d; return (int)sizeof(SavgolFilter) - 8600; }\n")
+    import subprocess
+    exe = tmp_path / "t"
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_create_validation_like_reference(capfd):
+    # ref: test/iterative/test_savgol.c:37-85
+    f = sg.SavgolFilter(5, 2)
+    assert f.window_size == 11
+    f.close()
+    sg.lib().savgol_destroy(None)
+    for bad in [dict(half_window=0, poly_order=2), dict(half_window=2, poly_order=10),
+                dict(half_window=5, poly_order=2, derivative=3), dict(half_window=33, poly_order=2),
+                dict(half_window=5, poly_order=2, time_step=0.0), dict(half_window=5, poly_order=4, derivative=5)]:
+        with pytest.raises(ValueError):
+            sg.SavgolFilter(**bad)
+    assert "savgol:" in capfd.readouterr().err
+
+
+def test_all_weight_tables_bit_identical_to_oracle(oracle):
+    cnt = 0
+    for n in range(1, 33):
+        for m in range(0, 2 * n + 1):
+            if 2 * n + m + 1 >= 76:
+                continue
+            for d in range(0, min(m, 4) + 1):
+                if m > 12 and (n + m + d) % 5:   # thin out the high-order tail
+                    continue
+                f = sg.SavgolFilter(n, m, d, 0.5)
+                o = oracle.Filter1D(n, m, d, 0.5)
+                assert np.array_equal(bits(f.center_weights), bits(o.center[: 2 * n + 1])), (n, m, d)
+                assert np.array_equal(bits(f.edge_weights), bits(o.edge)), (n, m, d)
+                assert np.float32(f.dt_scale) == np.float32(0.5) ** np.float32(d)
+                f.close()
+                cnt += 1
+    assert cnt > 1500
+
+
+def test_weight_properties_like_reference():
+    # ref: test/iterative/test_savgol.c:91-140
+    f = sg.SavgolFilter(5, 3)
+    w = f.center_weights
+    assert abs(w.sum() - 1.0) < 1e-5 and abs(w[0] - w[-1]) < 1e-6 and abs(w[1] - w[-2]) < 1e-6
+    g = sg.SavgolFilter(5, 3, 1).center_weights
+    assert abs(g[0] + g[-1]) < 1e-6 and abs(g[5]) < 1e-6
+
+
+def test_2d_weights_bit_identical_to_oracle(oracle):
+    for nx, ny, o, dx, dy in [(1, 1, 1, 0, 0), (2, 2, 2, 1, 0), (7, 7, 3, 0, 0), (2, 1, 2, 0, 1), (3, 4, 4, 1, 1),
+                              (16, 16, 6, 0, 0), (5, 3, 6, 2, 2), (7, 7, 3, 2, 0)]:
+        f = sg.Savgol2DFilter(nx, ny, o, dx, dy, 0.5, 2.0)
+        of = oracle.Filter2D(nx, ny, o, dx, dy, 0.5, 2.0)
+        assert np.array_equal(bits(f.weights), bits(of.W)), (nx, ny, o, dx, dy)
+        assert np.float32(f.scale) == np.float32(of.scale)
+        f.close()
+    # ref: test/iterative/test_savgol2d.c:27-71
+    for bad in [(0, 2, 2, 0, 0), (2, 2, 2, 2, 1), (1, 1, 6, 0, 0), (17, 2, 2, 0, 0), (2, 2, 7, 0, 0)]:
+        with pytest.raises(ValueError):
+            sg.Savgol2DFilter(*bad)
+
+
+def test_scalar_stream_shim_bit_identical_to_oracle(oracle):
+    # ref: test/iterative/test_savgol_stream.c:140-189 (stream == batch), here against the stream oracle
+    rng = np.random.default_rng(12345)
+    for n, m, d in [(5, 3, 0), (10, 2, 1), (2, 2, 2), (32, 4, 2)]:
+        x = rng.standard_normal(300).astype(np.float32)
+        s = sg.SavgolStream(n, m, d, 0.5)
+        assert s.latency == n and not s.ready
+        ys = []
+        for i, v in enumerate(x):
+            out = s.push_full(float(v))
+            assert (len(out) > 0) == (i >= 2 * n)
+            ys.extend(out)
+        ys.extend(s.flush())
+        assert len(ys) == x.size == s.samples_output and s.samples_received == x.size
+        ref = oracle.Filter1D(n, m, d, 0.5).stream_run(x)
+        assert np.array_equal(bits(np.array(ys, np.float32)), bits(ref))
+        # plain push: no leading edge, first valid output on sample 2n
+        s.reset()
+        got = [s.push(float(v)) for v in x[: 2 * n + 3]]
+        assert [g[1] for g in got] == [False] * (2 * n) + [True] * 3
+        assert np.float32(got[2 * n][0]) == ref[n]
+        s.close()
+
+
+def test_apply_fails_loudly_without_gpu(capfd):
+    if sg.device_ok():
+        pytest.skip("GPU present")
+    f = sg.SavgolFilter(5, 2)
+    x = np.zeros(100, np.float32)
+    with pytest.raises(RuntimeError):
+        f.apply(x)
+    assert "no CPU fallback" in capfd.readouterr().err
+    assert f.apply_valid(x).size == 0

@@ -1,0 +1,213 @@
+"""GPU parity tests of the 1D path: CUDA kernels called through the C ABI vs the oracle.
+
+Two bars (north_star): default (FMA) arithmetic within  max|d| <= 1e-6 * max|x| / dt^d  of the
+reference; `exact` arithmetic (reference summation order, unfused) bit-identical."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+import savgol_b200 as sg  # noqa: E402
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def tol(x, dt, d):
+    # north_star: max |delta| <= 1e-6 * max|x| * (1/dt^d)
+    return 1e-6 * float(np.max(np.abs(x))) / (dt ** d)
+
+
+@pytest.fixture(autouse=True)
+def _fast_mode():
+    sg.set_exact(False)
+    yield
+    sg.set_exact(False)
+
+
+MODES = ["polynomial", "reflect", "periodic", "constant"]
+CASES = [(1, 1, 0, 1.0), (2, 2, 1, 0.5), (3, 2, 2, 1.0), (5, 3, 0, 1.0), (6, 3, 0, 1.0), (7, 5, 3, 1.0), (10, 2, 1, 0.1),
+         (12, 4, 0, 1.0), (13, 4, 1, 1.0), (16, 3, 1, 0.01), (21, 6, 2, 1.0), (27, 3, 0, 1.0), (30, 5, 4, 2.0),
+         (31, 4, 1, 1.0), (32, 4, 2, 0.25)]
+
+
+@pytest.mark.parametrize("n,m,d,dt", CASES)
+def test_single_signal_all_modes_tolerance_and_exact(oracle, n, m, d, dt):
+    rng = np.random.default_rng(1000 * n + 10 * m + d)
+    for L in (2 * n + 1, 2 * n + 2, 100 + 3 * n, 4096, 4097, 4096 + n, 9000, 12289):
+        x = rng.standard_normal(L).astype(np.float32)
+        xd = torch.from_numpy(x).cuda()
+        for mode in MODES:
+            ref = oracle.Filter1D(n, m, d, dt, mode).apply(x)
+            f = sg.SavgolFilter(n, m, d, dt, mode)
+            y = f.apply(xd).cpu().numpy()
+            err = np.max(np.abs(y - ref))
+            assert err <= tol(x, dt, d), (n, m, d, L, mode, err, tol(x, dt, d))
+            sg.set_exact(True)
+            ye = f.apply(xd).cpu().numpy()
+            sg.set_exact(False)
+            assert np.array_equal(bits(ye), bits(ref)), (n, m, d, L, mode, int(np.argmax(bits(ye) != bits(ref))))
+            f.close()
+
+
+def test_config2_shape_batch_reflect(oracle):
+    # BASELINE config 2 at reduced batch: signals x 4096, n16 m3 d1 REFLECT
+    rng = np.random.default_rng(1)
+    rows, L = 512, 4096
+    t = np.arange(L, dtype=np.float32)
+    x = (rng.standard_normal((rows, L)) + np.sin(0.01 * t)[None, :] * rng.uniform(0.5, 2, (rows, 1))).astype(np.float32)
+    f = sg.SavgolFilter(16, 3, 1, 1.0, "reflect")
+    ref = oracle.Filter1D(16, 3, 1, 1.0, "reflect").apply(x)
+    y = f.apply(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert np.max(np.abs(y - ref)) <= tol(x, 1.0, 1)
+    sg.set_exact(True)
+    ye = f.apply(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert np.array_equal(bits(ye), bits(ref))
+
+
+def test_config1_shape_polynomial_1m(oracle):
+    # BASELINE config 1: one 1,000,000-sample signal, n12 m4 d0, polynomial edges
+    rng = np.random.default_rng(0)
+    L = 1_000_000
+    x = (np.sin(1e-3 * np.arange(L)) + 0.1 * (rng.random(L) - 0.5)).astype(np.float32)
+    f = sg.SavgolFilter(12, 4, 0, 1.0, "polynomial")
+    ref = oracle.Filter1D(12, 4, 0, 1.0, "polynomial").apply(x)
+    y = f.apply(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert np.max(np.abs(y - ref)) <= tol(x, 1.0, 0)
+    sg.set_exact(True)
+    assert np.array_equal(bits(f.apply(torch.from_numpy(x).cuda()).cpu().numpy()), bits(ref))
+
+
+def test_matlab_known_answer_on_gpu(golden_dir):
+    import os
+    z = np.load(os.path.join(golden_dir, "matlab_n6_m3.npz"))
+    f = sg.SavgolFilter(6, 3, 0, 1.0, "polynomial")
+    y = f.apply(torch.from_numpy(z["raw"]).cuda()).cpu().numpy()
+    assert np.max(np.abs(y - z["expected"])) < 1e-5
+    yh = f.apply(z["raw"].copy())  # host pointer path
+    assert np.array_equal(bits(yh), bits(y))
+
+
+def test_golden_reference_outputs_exact(golden_dir):
+    import os
+    G = np.load(os.path.join(golden_dir, "ref_outputs.npz"))
+    sg.set_exact(True)
+    for ci, (n, m, d, dt) in enumerate(G["cases"]):
+        x = torch.from_numpy(G[f"c{ci}_x"]).cuda()
+        for b in range(4):
+            f = sg.SavgolFilter(int(n), int(m), int(d), float(dt), b)
+            assert np.array_equal(bits(f.apply(x).cpu().numpy()), bits(G[f"c{ci}_apply_b{b}"])), (ci, b)
+            if b == 0:
+                assert np.array_equal(bits(f.apply_valid(x).cpu().numpy()), bits(G[f"c{ci}_valid"])), ci
+            f.close()
+
+
+def test_pitched_batch_and_short_rows(oracle):
+    rng = np.random.default_rng(5)
+    f = sg.SavgolFilter(4, 2, 0, 1.0, "constant")
+    o = oracle.Filter1D(4, 2, 0, 1.0, "constant")
+    big = torch.from_numpy(rng.standard_normal((37, 301)).astype(np.float32)).cuda()
+    view = big[:, 3:250]  # pitch 301, length 247, misaligned start
+    out = torch.zeros_like(big)
+    f.apply(view, out=out[:, 5:252])
+    ref = o.apply(view.cpu().numpy().copy())
+    assert np.max(np.abs(out[:, 5:252].cpu().numpy() - ref)) <= tol(ref, 1.0, 0) * 4
+    assert torch.all(out[:, :5] == 0) and torch.all(out[:, 252:] == 0)
+
+
+def test_error_returns_like_reference(capfd):
+    f = sg.SavgolFilter(5, 2)
+    lib = sg.lib()
+    x = torch.zeros(100, device="cuda")
+    assert lib.savgol_apply(f.handle, x.data_ptr(), x.data_ptr(), 10) == -1      # ref: src/savgolFilter.c:751-755
+    assert lib.savgol_apply(f.handle, None, x.data_ptr(), 100) == -1              # ref: :746-749
+    assert lib.savgol_apply_valid(f.handle, x.data_ptr(), 10, x.data_ptr()) == 0  # ref: :833-835
+    assert lib.savgol_apply_strided(f.handle, x.data_ptr(), 4, 0, x.data_ptr(), 4, 0, 10) == -1
+    err = capfd.readouterr().err
+    assert "NULL pointer" in err and "window size" in err
+
+
+def test_in_place_gives_out_of_place_result(oracle):
+    # DESIGN.md "in-place": alias-safe, equals the out-of-place result
+    rng = np.random.default_rng(9)
+    for L in (500, 4096, 20000):
+        x = rng.standard_normal(L).astype(np.float32)
+        for mode in ("polynomial", "reflect"):
+            f = sg.SavgolFilter(8, 3, 0, 1.0, mode)
+            ref = oracle.Filter1D(8, 3, 0, 1.0, mode).apply(x)
+            xd = torch.from_numpy(x).cuda()
+            f.apply(xd, out=xd)
+            assert np.max(np.abs(xd.cpu().numpy() - ref)) <= tol(x, 1.0, 0), (L, mode)
+
+
+def test_strided_struct_field(oracle):
+    # ref: test/iterative/test_savgol.c:245-294 -- 12-byte records, float field at offset 4
+    rng = np.random.default_rng(11)
+    for L in (11, 360, 5000):
+        x = rng.standard_normal(L).astype(np.float32)
+        rec = np.zeros(3 * L, np.float32); rec[1::3] = x
+        f = sg.SavgolFilter(5, 2, 1, 0.5, "reflect")      # boundary is ignored by strided (Q3)
+        o = oracle.Filter1D(5, 2, 1, 0.5, "polynomial")
+        ref = o.apply(x)
+        # device records
+        rin = torch.from_numpy(rec).cuda()
+        rout = torch.full((3 * L,), -7.0, device="cuda")
+        assert f.apply_strided(rin.data_ptr(), 12, 4, rout.data_ptr(), 12, 4, L) == 0
+        got = rout.cpu().numpy()
+        assert np.max(np.abs(got[1::3] - ref)) <= tol(x, 0.5, 1)
+        assert np.all(got[0::3] == -7.0) and np.all(got[2::3] == -7.0)
+        # host records
+        hout = np.full(3 * L, -7.0, np.float32)
+        assert f.apply_strided(rec.ctypes.data, 12, 4, hout.ctypes.data, 12, 4, L) == 0
+        assert np.array_equal(bits(hout), bits(got))
+        # exact
+        sg.set_exact(True)
+        rout.fill_(-7.0)
+        assert f.apply_strided(rin.data_ptr(), 12, 4, rout.data_ptr(), 12, 4, L) == 0
+        assert np.array_equal(bits(rout.cpu().numpy()[1::3]), bits(ref))
+        sg.set_exact(False)
+
+
+def test_halo_slices_reassemble_full_signal(oracle):
+    # the per-GPU piece of a partitioned long signal (BASELINE config 3 shape: n32 m4 d2 periodic)
+    rng = np.random.default_rng(3)
+    n, L, parts = 32, 40000, 5
+    x = rng.standard_normal(L).astype(np.float32)
+    xd = torch.from_numpy(x).cuda()
+    for mode in MODES:
+        f = sg.SavgolFilter(n, 4, 2, 1.0, mode)
+        ref = oracle.Filter1D(n, 4, 2, 1.0, mode).apply(x)
+        sg.set_exact(True)
+        cuts = [0, 7000, 16001, 16100, 30000, L]
+        out = torch.empty_like(xd)
+        for p in range(parts):
+            a, b = cuts[p], cuts[p + 1]
+            if mode == "periodic":
+                left = xd[a - n:a] if a > 0 else xd[L - n:]
+                right = xd[b:b + n] if b < L else xd[:n]
+            else:
+                left = xd[a - n:a] if a > 0 else None
+                right = xd[b:b + n] if b < L else None
+            f.apply_halo(xd[a:b], left.contiguous() if left is not None else None,
+                         right.contiguous() if right is not None else None, out=out[a:b])
+        sg.set_exact(False)
+        assert np.array_equal(bits(out.cpu().numpy()), bits(ref)), mode
+
+
+def test_host_pointer_path_chunks(oracle):
+    rng = np.random.default_rng(4)
+    f = sg.SavgolFilter(16, 3, 1, 1.0, "reflect")
+    o = oracle.Filter1D(16, 3, 1, 1.0, "reflect")
+    x = rng.standard_normal((300, 4096)).astype(np.float32)
+    y = f.apply(x)
+    assert isinstance(y, np.ndarray)
+    assert np.max(np.abs(y - o.apply(x))) <= tol(x, 1.0, 1)
+    # pinned host memory
+    xp = torch.from_numpy(x).pin_memory()
+    yp = torch.empty_like(xp).pin_memory()
+    f.apply(xp, out=yp)
+    assert np.array_equal(bits(yp.numpy()), bits(y))
