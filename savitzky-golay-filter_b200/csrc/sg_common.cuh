@@ -47,7 +47,8 @@ struct Args1D {
     float scale;             // 1/dt^d, applied as a separate multiply like the reference
     int mode;                // MODE_* used where a halo pointer is null
     int edge_lead, edge_trail;  // 1: outputs [0,n) / [len-n,len) come from the polynomial edge table
-    long long tiles_per_row, ntiles;
+    long long tiles_per_row, ntiles;  // ntiles < 2^31 (checked by the launcher)
+    int tpr;                 // threads per row slot: 128 (long rows), 64 (len <= 2048), 32 (len <= 1024)
 };
 
 // ---------------------------------------------------------------------------------------------
