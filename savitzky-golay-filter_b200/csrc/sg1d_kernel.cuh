@@ -98,41 +98,40 @@ __device__ __forceinline__ float virtual_sample(const Args1D& a, const char* xro
     return p ? *p : 0.0f;
 }
 
-// Stage one row slot: shared position 4c <-> x index o0 - PAD + 4c.  `p` is the thread's index
-// inside the slot's group of `tpr` threads.  Everything is asynchronous (cp.async), so no thread
-// waits on a global load here:
+// Stage one segment (kSeg outputs of one row, plus halo) into a warp's buffer: shared position 4c
+// <-> x index o0 - PAD + 4c.  Everything is asynchronous (cp.async), so no lane waits on a global
+// load here:
 //   * chunks whose four samples exist are copied 16 bytes at a time (4 x 4 bytes when the row is
-//     misaligned or strided),
-//   * the remaining elements -- virtual pad samples, ragged ends, alignment slack -- are spread one
-//     element per thread over the slot (the "edge path"): each thread maps its element to the
-//     address the boundary rule designates and copies 4 bytes, or stores 0.
+//     misaligned or strided): 8 full passes of the warp plus a tail,
+//   * the remaining elements -- virtual pad samples, ragged ends, alignment slack -- form the
+//     "edge path": one element per lane, each lane maps its element to the address the boundary
+//     rule designates and copies 4 bytes, or stores 0.
 template <int LEAD, int N>
-__device__ __forceinline__ void stage_slot(float4* slot_buf, const Args1D& a, long long row, long long o0, int nch,
-                                           int p, int tpr)
+__device__ __forceinline__ void stage_segment(float4* buf, const Args1D& a, const char* xrow, long long row,
+                                              long long o0, int nch, int lane)
 {
     constexpr int PAD = Geo<LEAD>::PAD;
-    const char* xrow = a.in + row * a.in_row_bytes;
     const long long xi0 = o0 - PAD;
     const int c_lo = o0 >= PAD ? 0 : static_cast<int>((PAD - o0) >> 2);
     const long long chi = (a.len - xi0) >> 2;  // chunks whose four samples all exist end here
     const int c_hi = static_cast<int>(chi < nch ? chi : nch);
     const char* src0 = xrow + xi0 * a.in_stride;  // only dereferenced for chunks inside [c_lo, c_hi)
     const bool vec_ok = (a.in_stride == 4) && ((reinterpret_cast<uintptr_t>(src0) & 15) == 0);
-    float4* dst0 = slot_buf + p + (p >> 3);
-    const int dstep = tpr + (tpr >> 3);  // (c + tpr) + ((c + tpr) >> 3) - (c + (c >> 3)), tpr % 8 == 0
+    float4* dst0 = buf + lane + (lane >> 3);  // chunk c = lane + 32*it lives at c + (c >> 3) = dst0 + 36*it
     if (vec_ok) {
+        const char* s = src0 + lane * 16;
 #pragma unroll
         for (int it = 0; it < 9; ++it) {
-            const int c = p + it * tpr;
-            if (c >= c_lo && c < c_hi) cp_async16(dst0 + it * dstep, src0 + static_cast<long long>(c) * 16);
+            const int c = lane + 32 * it;
+            if (c >= c_lo && c < c_hi) cp_async16(dst0 + 36 * it, s + 512 * it);
         }
     } else {
         const long long st = a.in_stride;
 #pragma unroll 1
         for (int it = 0; it < 9; ++it) {
-            const int c = p + it * tpr;
+            const int c = lane + 32 * it;
             if (c >= c_lo && c < c_hi) {
-                float* d = reinterpret_cast<float*>(dst0 + it * dstep);
+                float* d = reinterpret_cast<float*>(dst0 + 36 * it);
                 const char* sp = src0 + 4LL * c * st;
                 cp_async4(d, sp); cp_async4(d + 1, sp + st); cp_async4(d + 2, sp + 2 * st); cp_async4(d + 3, sp + 3 * st);
             }
@@ -140,10 +139,10 @@ __device__ __forceinline__ void stage_slot(float4* slot_buf, const Args1D& a, lo
     }
     const int nl = 4 * c_lo, nrest = nl + 4 * (nch - c_hi);
 #pragma unroll 1
-    for (int q = p; q < nrest; q += tpr) {
-        const int el = q < nl ? q : 4 * c_hi + (q - nl);  // element index inside the slot
+    for (int q = lane; q < nrest; q += 32) {
+        const int el = q < nl ? q : 4 * c_hi + (q - nl);  // element index inside the segment buffer
         const int c = el >> 2;
-        float* d = reinterpret_cast<float*>(slot_buf + c + (c >> 3)) + (el & 3);
+        float* d = reinterpret_cast<float*>(buf + c + (c >> 3)) + (el & 3);
         const float* sp = sample_address<LEAD, N>(a, xrow, row, xi0 + el);
         if (sp) cp_async4(d, sp);
         else *d = 0.0f;
@@ -247,15 +246,19 @@ __device__ __forceinline__ void compute_exact(const float4* __restrict__ sb, con
 }
 
 // ---------------------------------------------------------------------------------------------
-// Tile geometry.  A CTA of 128 threads owns 4096 outputs per iteration, arranged as `rpt` row
-// slots of `tpr` threads (tpr = 128, 64 or 32 -> one long-row tile, or 2 / 4 short rows of at
-// most 2048 / 1024 samples).  Every slot has its own halo in shared memory.
+// Warp-autonomous pipeline.  The unit of work is a SEGMENT: kSeg = 1024 consecutive outputs of one
+// row (32 lanes x 32 outputs) together with its halo.  Every warp owns two private segment buffers
+// and loops over segments gw, gw + W, gw + 2W, ... (W = warps in the grid): it issues the cp.async
+// copies of its NEXT segment, waits for the CURRENT one (cp.async.wait_group + __syncwarp), computes,
+// stores.  Warps never synchronise with each other -- there is no __syncthreads in the kernel -- so a
+// warp that is waiting on HBM never holds up the FMA pipe of its neighbours, and with ~20 resident
+// warps per SM about 80 KB of loads are in flight per SM at any time.
+constexpr int kSeg = 32 * kR;  // 1024 outputs per segment
+
 template <int N, int DELTA>
 struct Smem1D {
-    static constexpr int nch(int seg) { return (seg + 2 * N + DELTA + 3) / 4; }
-    static constexpr int phys(int seg) { return nch(seg) + (nch(seg) >> 3) + 1; }
-    static constexpr int cmax(int a, int b) { return a > b ? a : b; }
-    static constexpr int kBufChunks = cmax(phys(4096), cmax(2 * phys(2048), 4 * phys(1024)));
+    static constexpr int kSegChunks = (kSeg + 2 * N + DELTA + 3) / 4;
+    static constexpr int kSegPhys = kSegChunks + (kSegChunks >> 3) + 1;
 };
 
 template <int N, bool LEAD2N, int ARITH>
@@ -264,114 +267,110 @@ __global__ void __launch_bounds__(kThreads, SG_MIN_BLOCKS) sg1d_kernel(const __g
     constexpr int LEAD = LEAD2N ? 2 * N : N;
     constexpr int DELTA = Geo<LEAD>::DELTA;
     constexpr int WS = 2 * N + 1;
+    constexpr int kWarps = kThreads / 32;
     using SM = Smem1D<N, DELTA>;
 
-    __shared__ float4 s_buf[2][SM::kBufChunks];
-    __shared__ float s_edge[4][2 * kMaxN];
+    __shared__ float4 s_buf[kWarps][2][SM::kSegPhys];
+    __shared__ float s_edge[kWarps][2 * kMaxN];
 
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int tpr = a.tpr;                 // threads per row slot (32, 64, 128)
-    const int slot = tid / tpr;            // row slot of this thread
-    const int p = tid - slot * tpr;        // index inside the slot
-    const int seg = tpr * kR;              // outputs per slot
-    const int slot_chunks = ((seg + 2 * N + DELTA + 3) >> 2);
-    const int slot_phys = slot_chunks + (slot_chunks >> 3) + 1;
-    const int rpt = kThreads / tpr;
-    const unsigned tiles_per_row = static_cast<unsigned>(a.tiles_per_row);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const unsigned nseg = static_cast<unsigned>(a.ntiles);           // segments in the launch
+    const unsigned spr = static_cast<unsigned>(a.tiles_per_row);     // segments per row
+    const unsigned stride = gridDim.x * kWarps;
+    const long long len = a.len;
 
-#define SG_LOCATE(tile_, row_, o0_)                                                                  \
-    do {                                                                                            \
-        if (tiles_per_row == 1) { row_ = static_cast<long long>(tile_) * rpt + slot; o0_ = 0; }    \
-        else { const unsigned r_ = (tile_) / tiles_per_row; row_ = r_;                              \
-               o0_ = static_cast<long long>((tile_) - r_ * tiles_per_row) * kTile; }                \
+    unsigned seg = blockIdx.x * kWarps + warp;
+    long long row = 0, o0 = 0;
+    const char* xrow = nullptr;
+    int nch = 0;
+    // segment index -> row, first output, row base, number of 16-byte chunks to stage
+#define SG_LOCATE(seg_, row_, o0_, xrow_, nch_)                                                       \
+    do {                                                                                             \
+        unsigned r_ = (seg_), t_ = 0;                                                                \
+        if (spr != 1) { r_ = (seg_) / spr; t_ = (seg_) - r_ * spr; }                                 \
+        row_ = r_;                                                                                   \
+        o0_ = static_cast<long long>(t_) * kSeg;                                                     \
+        xrow_ = a.in + row_ * a.in_row_bytes;                                                        \
+        const long long left_ = len - o0_;                                                           \
+        nch_ = (static_cast<int>(left_ < kSeg ? left_ : kSeg) + 2 * N + DELTA + 3) >> 2;             \
     } while (0)
-#define SG_CHUNKS_OF(o0_) static_cast<int>(((a.len - (o0_) > seg ? seg : a.len - (o0_)) + 2 * N + DELTA + 3) >> 2)
 
-    const unsigned ntiles = static_cast<unsigned>(a.ntiles);
-    unsigned tile = blockIdx.x;
-    long long row, o0;
-    if (tile < ntiles) {
-        SG_LOCATE(tile, row, o0);
-        if (row < a.rows) stage_slot<LEAD, N>(s_buf[0] + slot * slot_phys, a, row, o0, SG_CHUNKS_OF(o0), p, tpr);
+    if (seg < nseg) {
+        SG_LOCATE(seg, row, o0, xrow, nch);
+        stage_segment<LEAD, N>(s_buf[warp][0], a, xrow, row, o0, nch, lane);
     }
     cp_async_commit();
 
-    for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
-        SG_LOCATE(tile, row, o0);
-        const bool active = row < a.rows;
-        const char* xrow = a.in + row * a.in_row_bytes;
-
-        // prefetch the next tile of this CTA into the other buffer
-        const unsigned nxt = tile + gridDim.x;
-        if (nxt < ntiles) {
-            long long nrow, no0;
-            SG_LOCATE(nxt, nrow, no0);
-            if (nrow < a.rows) stage_slot<LEAD, N>(s_buf[(it + 1) & 1] + slot * slot_phys, a, nrow, no0, SG_CHUNKS_OF(no0), p, tpr);
+    for (int it = 0; seg < nseg; ++it, seg += stride) {
+        // prefetch this warp's next segment into its other buffer
+        const unsigned nxt = seg + stride;
+        long long nrow = 0, no0 = 0;
+        const char* nxrow = nullptr;
+        int nnch = 0;
+        if (nxt < nseg) {
+            SG_LOCATE(nxt, nrow, no0, nxrow, nnch);
+            stage_segment<LEAD, N>(s_buf[warp][(it + 1) & 1], a, nxrow, nrow, no0, nnch, lane);
         }
         cp_async_commit();
 
-        // polynomial edge outputs of this slot's row (global reads, independent of the staged tile):
-        // the slot's first warp evaluates the leading edge, its second warp (or the same one when the
-        // slot is a single warp) the trailing edge, one lane per output.
-        const bool lead_tile = active && a.edge_lead && o0 < N;
-        const bool trail_tile = active && a.edge_trail && (o0 + seg > a.len - N);
-        const int warp_in_slot = p >> 5;
-        if (lead_tile && warp_in_slot == 0 && lane < N) {
-            // out[e] = scale * sum_k E[e][k] * x[2n-k]   ref: src/savgolFilter.c:773-777, 593-623
+        // polynomial edge outputs that fall into this segment (global reads, independent of the
+        // staged data): one lane per output.  ref: src/savgolFilter.c:769-784
+        const bool lead_seg = a.edge_lead && o0 < N;
+        const bool trail_seg = a.edge_trail && (o0 + kSeg > len - N);
+        if (lead_seg && lane < N) {
+            // out[e] = scale * sum_k E[e][k] * x[2n-k]   (reversed traversal, ref :593-623)
             const float s = dot_ordered<WS, ARITH>([&](int k) { return a.edge_t[k * 32 + lane]; },
                                                    [&](int k) { return ld_sample(xrow, a.in_stride, 2 * N - k); });
-            s_edge[slot][lane] = ARITH == ARITH_FAST ? s * a.scale : __fmul_rn(s, a.scale);
+            s_edge[warp][lane] = ARITH == ARITH_FAST ? s * a.scale : __fmul_rn(s, a.scale);
         }
-        if (trail_tile && warp_in_slot == (tpr > 32 ? 1 : 0) && lane < N) {
-            // out[len-1-e] = scale * sum_k E[e][k] * x[len-ws+k]   ref: src/savgolFilter.c:780-784
-            const long long base = a.len - WS;
+        if (trail_seg && lane < N) {
+            // out[len-1-e] = scale * sum_k E[e][k] * x[len-ws+k]
+            const long long base = len - WS;
             const float s = dot_ordered<WS, ARITH>([&](int k) { return a.edge_t[k * 32 + lane]; },
                                                    [&](int k) { return ld_sample(xrow, a.in_stride, base + k); });
-            s_edge[slot][kMaxN + lane] = ARITH == ARITH_FAST ? s * a.scale : __fmul_rn(s, a.scale);
+            s_edge[warp][kMaxN + lane] = ARITH == ARITH_FAST ? s * a.scale : __fmul_rn(s, a.scale);
         }
 
-        cp_async_wait<1>();
-        __syncthreads();
+        cp_async_wait<1>();  // this lane's copies of the current segment have landed ...
+        __syncwarp();        // ... and so have the other lanes' (and their s_edge entries)
 
-        const float4* sb = s_buf[it & 1] + slot * slot_phys + 9 * p;
+        const float4* sb = s_buf[warp][it & 1] + 9 * lane;
         float out[kR];
         if constexpr (ARITH == ARITH_FAST) compute_fast<N, DELTA>(sb, W, a.scale, out);
         else compute_exact<N, DELTA, ARITH>(sb, W, a.scale, out);
 
-        const long long o = o0 + static_cast<long long>(kR) * p;
-        if (lead_tile || trail_tile) {
+        const long long o = o0 + kR * lane;
+        if (lead_seg || trail_seg) {
 #pragma unroll
             for (int j = 0; j < kR; ++j) {
                 const long long oj = o + j;
-                if (lead_tile && oj < N) out[j] = s_edge[slot][oj];
-                else if (trail_tile && oj >= a.len - N && oj < a.len) out[j] = s_edge[slot][kMaxN + (a.len - 1 - oj)];
+                if (lead_seg && oj < N) out[j] = s_edge[warp][oj];
+                else if (trail_seg && oj >= len - N && oj < len) out[j] = s_edge[warp][kMaxN + (len - 1 - oj)];
             }
         }
 
-        if (active) {
-            // stream: hand the last state_w samples of [lead pad | x] to the next chunk
-            if (a.state_out != nullptr && o0 + seg >= a.len)
-                for (int i = p; i < a.state_w; i += tpr)
-                    a.state_out[row * a.state_pitch + i] = virtual_sample<LEAD, N>(a, xrow, row, a.len - a.state_w + i);
+        // stream: hand the last state_w samples of [lead pad | x] to the next chunk
+        if (a.state_out != nullptr && o0 + kSeg >= len)
+            for (int i = lane; i < a.state_w; i += 32)
+                a.state_out[row * a.state_pitch + i] = virtual_sample<LEAD, N>(a, xrow, row, len - a.state_w + i);
 
-            char* orow = a.out + row * a.out_row_bytes;
-            if (a.out_stride == 4 && o + kR <= a.out_len && ((reinterpret_cast<uintptr_t>(orow) + static_cast<uintptr_t>(o * 4)) & 15) == 0) {
-                float* dst = reinterpret_cast<float*>(orow) + o;
+        char* orow = a.out + row * a.out_row_bytes;
+        if (a.out_stride == 4 && o + kR <= a.out_len && ((reinterpret_cast<uintptr_t>(orow) + static_cast<uintptr_t>(o * 4)) & 15) == 0) {
+            float* dst = reinterpret_cast<float*>(orow) + o;
 #pragma unroll
-                for (int q = 0; q < kR / 4; ++q)
-                    st_cs_f4(dst + 4 * q, make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]));
-            } else {
+            for (int q = 0; q < kR / 4; ++q)
+                st_cs_f4(dst + 4 * q, make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]));
+        } else {
 #pragma unroll
-                for (int j = 0; j < kR; ++j)
-                    if (o + j < a.out_len) *reinterpret_cast<float*>(orow + (o + j) * a.out_stride) = out[j];
-            }
+            for (int j = 0; j < kR; ++j)
+                if (o + j < a.out_len) *reinterpret_cast<float*>(orow + (o + j) * a.out_stride) = out[j];
         }
-        __syncthreads();  // everyone is done with s_buf[it&1] and s_edge before they are refilled
+        __syncwarp();  // all lanes are done with s_buf[warp][it&1] and s_edge[warp] before the refill
+        row = nrow; o0 = no0; xrow = nxrow; nch = nnch;
     }
     cp_async_wait<0>();
 #undef SG_LOCATE
-#undef SG_CHUNKS_OF
 }
 
 }  // namespace sg

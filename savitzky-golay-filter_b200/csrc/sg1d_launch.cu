@@ -60,16 +60,15 @@ cudaError_t sg1d_launch(int n, int variant, const W1D& w, Args1D& a, cudaStream_
         sms = dev < 64 ? g_sms[dev] : 148;
     }
 
-    // short rows share a tile: 4 rows of <= 1024 samples or 2 rows of <= 2048 samples per CTA iteration
-    a.tpr = a.len <= 1024 ? 32 : a.len <= 2048 ? 64 : 128;
-    const long long rows_per_tile = kThreads / a.tpr;
+    // work unit = segment of kTile (1024) outputs of one row, one warp each
     a.tiles_per_row = (a.len + kTile - 1) / kTile;
-    a.ntiles = a.tiles_per_row > 1 ? a.tiles_per_row * a.rows : (a.rows + rows_per_tile - 1) / rows_per_tile;
+    a.ntiles = a.tiles_per_row * a.rows;
     if (a.ntiles <= 0) return cudaSuccess;
-    if (a.ntiles >= (1LL << 31)) return cudaErrorInvalidValue;
+    if (a.ntiles >= (1LL << 31) - (1LL << 20)) return cudaErrorInvalidValue;
     // persistent CTAs: one per resident slot (148 SMs x blocks/SM on a B200), round-robin over tiles
     long long grid = static_cast<long long>(sms) * bps;
-    if (grid > a.ntiles) grid = a.ntiles;
+    const long long need = (a.ntiles + kThreads / 32 - 1) / (kThreads / 32);
+    if (grid > need) grid = need;
     k.kernel<<<static_cast<unsigned>(grid), kThreads, 0, stream>>>(w, a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();

@@ -9,7 +9,7 @@ namespace sg {
 
 constexpr int kThreads = 128;              // 4 warps per CTA
 constexpr int kR = 32;                     // consecutive outputs per thread (register sliding window)
-constexpr int kTile = kThreads * kR;       // 4096 outputs per tile
+constexpr int kTile = 32 * kR;             // 1024 outputs per segment (one warp)
 constexpr int kMaxN = 32;
 constexpr int kMaxWs = 2 * kMaxN + 1;      // 65, ref: include/iterative/savgolFilter.h:42
 
@@ -47,8 +47,7 @@ struct Args1D {
     float scale;             // 1/dt^d, applied as a separate multiply like the reference
     int mode;                // MODE_* used where a halo pointer is null
     int edge_lead, edge_trail;  // 1: outputs [0,n) / [len-n,len) come from the polynomial edge table
-    long long tiles_per_row, ntiles;  // ntiles < 2^31 (checked by the launcher)
-    int tpr;                 // threads per row slot: 128 (long rows), 64 (len <= 2048), 32 (len <= 1024)
+    long long tiles_per_row, ntiles;  // segments (1024 outputs) per row / in the launch; ntiles < 2^31
 };
 
 // ---------------------------------------------------------------------------------------------
