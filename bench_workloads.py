@@ -141,14 +141,15 @@ def run_1d_family(wl, args, sg, lib, torch, np, dev, rank, world, barrier, max_o
         rows, K = wl["rows"], wl["length"]
         s = sg.SavgolMCStream(rows, n, m, d, dt)
         x = _synthetic_batch(torch, rows, K, dev, 4 + rank)
-        y = torch.empty(rows, K + n, device=dev)
+        OP = (K + n + 3) & ~3  # output pitch: >= K + half_window, 16-byte aligned rows
+        y = torch.empty(rows, OP, device=dev)
         xp, yp = x.data_ptr(), y.data_ptr()
-        k0 = lib.savgol_mcstream_push(s._h, xp, K, K, yp, K + n)   # first fill (leading edge), outside the timed region
+        k0 = lib.savgol_mcstream_push(s._h, xp, K, K, yp, OP)   # first fill (leading edge), outside the timed region
         assert k0 == K - n
         y0 = y[:32, :K - n].cpu().numpy().copy()
 
         def call():
-            k = lib.savgol_mcstream_push(s._h, xp, K, K, yp, K + n)
+            k = lib.savgol_mcstream_push(s._h, xp, K, K, yp, OP)
             assert k == K
         units = rows * K
         res["kernel"] = f"sg1d_kernel<N={n},stream,FFMA2>"
@@ -176,7 +177,7 @@ def run_1d_family(wl, args, sg, lib, torch, np, dev, rank, world, barrier, max_o
     if kind == "stream":
         # re-establish "first chunk then one more" so that parity() sees [chunk | chunk]
         s.reset()
-        lib.savgol_mcstream_push(s._h, xp, K, K, yp, K + n)
+        lib.savgol_mcstream_push(s._h, xp, K, K, yp, OP)
         y0 = y[:32, :K - n].cpu().numpy().copy()
         call()
         res["parity"] = parity() if rank == 0 else None

@@ -29,7 +29,7 @@
 #include "sg_common.cuh"
 
 #ifndef SG_MIN_BLOCKS
-#define SG_MIN_BLOCKS 5  // resident CTAs per SM the register allocator must allow
+#define SG_MIN_BLOCKS 4  // resident CTAs per SM the register allocator must allow
 #endif
 
 namespace sg {
@@ -107,22 +107,25 @@ __device__ __forceinline__ float virtual_sample(const Args1D& a, const char* xro
 //     "edge path": one element per lane, each lane maps its element to the address the boundary
 //     rule designates and copies 4 bytes, or stores 0.
 template <int LEAD, int N>
-__device__ __forceinline__ void stage_segment(float4* buf, const Args1D& a, const char* xrow, long long row,
-                                              long long o0, int nch, int lane)
+__device__ __forceinline__ void stage_segment(float4* dst0 /* buf + lane + (lane >> 3) */, float4* buf, const Args1D& a,
+                                              const char* xrow, long long row, long long o0, int left /* min(len-o0, big) */,
+                                              bool rows_aligned, int lane)
 {
     constexpr int PAD = Geo<LEAD>::PAD;
-    const long long xi0 = o0 - PAD;
-    const int c_lo = o0 >= PAD ? 0 : static_cast<int>((PAD - o0) >> 2);
-    const long long chi = (a.len - xi0) >> 2;  // chunks whose four samples all exist end here
-    const int c_hi = static_cast<int>(chi < nch ? chi : nch);
-    const char* src0 = xrow + xi0 * a.in_stride;  // only dereferenced for chunks inside [c_lo, c_hi)
-    const bool vec_ok = (a.in_stride == 4) && ((reinterpret_cast<uintptr_t>(src0) & 15) == 0);
-    float4* dst0 = buf + lane + (lane >> 3);  // chunk c = lane + 32*it lives at c + (c >> 3) = dst0 + 36*it
+    constexpr int DELTA = Geo<LEAD>::DELTA;
+    // segment-local 32-bit bookkeeping: chunk c covers x indices o0 - PAD + 4c .. +3
+    const int nout = left < kSeg ? left : kSeg;
+    const int nch = (nout + 2 * N + DELTA + 3) >> 2;          // chunks the compute loop may touch
+    const int c_lo = o0 == 0 ? PAD / 4 : 0;                    // first chunk made of four existing samples
+    const int c_all = (left + PAD) >> 2;                       // chunks that end inside the row
+    const int c_hi = c_all < nch ? c_all : nch;
+    const char* src0 = xrow + (o0 - PAD) * a.in_stride;        // only dereferenced inside [c_lo, c_hi)
+    const bool vec_ok = rows_aligned || ((a.in_stride == 4) && ((reinterpret_cast<uintptr_t>(src0) & 15) == 0));
     if (vec_ok) {
         const char* s = src0 + lane * 16;
 #pragma unroll
         for (int it = 0; it < 9; ++it) {
-            const int c = lane + 32 * it;
+            const int c = lane + 32 * it;  // chunk c lives at c + (c >> 3) = dst0 + 36*it
             if (c >= c_lo && c < c_hi) cp_async16(dst0 + 36 * it, s + 512 * it);
         }
     } else {
@@ -143,7 +146,7 @@ __device__ __forceinline__ void stage_segment(float4* buf, const Args1D& a, cons
         const int el = q < nl ? q : 4 * c_hi + (q - nl);  // element index inside the segment buffer
         const int c = el >> 2;
         float* d = reinterpret_cast<float*>(buf + c + (c >> 3)) + (el & 3);
-        const float* sp = sample_address<LEAD, N>(a, xrow, row, xi0 + el);
+        const float* sp = sample_address<LEAD, N>(a, xrow, row, o0 - PAD + el);
         if (sp) cp_async4(d, sp);
         else *d = 0.0f;
     }
@@ -253,7 +256,7 @@ __device__ __forceinline__ void compute_exact(const float4* __restrict__ sb, con
 // stores.  Warps never synchronise with each other -- there is no __syncthreads in the kernel -- so a
 // warp that is waiting on HBM never holds up the FMA pipe of its neighbours, and with ~20 resident
 // warps per SM about 80 KB of loads are in flight per SM at any time.
-constexpr int kSeg = 32 * kR;  // 1024 outputs per segment
+
 
 template <int N, int DELTA>
 struct Smem1D {
@@ -275,42 +278,44 @@ __global__ void __launch_bounds__(kThreads, SG_MIN_BLOCKS) sg1d_kernel(const __g
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const unsigned nseg = static_cast<unsigned>(a.ntiles);           // segments in the launch
-    const unsigned spr = static_cast<unsigned>(a.tiles_per_row);     // segments per row
-    const unsigned stride = gridDim.x * kWarps;
+    const unsigned nseg = static_cast<unsigned>(a.ntiles);        // segments in the launch
+    const unsigned spr = static_cast<unsigned>(a.tiles_per_row);  // segments per row
+    const unsigned stride = gridDim.x * kWarps;                   // segments between two iterations of a warp
     const long long len = a.len;
+    // rows whose base and pitch are 16-byte aligned keep every segment start aligned (o0 and PAD are
+    // multiples of 4 samples): decide once instead of per segment
+    const bool rows_aligned = a.in_stride == 4 && ((reinterpret_cast<uintptr_t>(a.in) | static_cast<uintptr_t>(a.in_row_bytes)) & 15) == 0;
+    constexpr int kBig = kSeg + 4 * kMaxWs;  // "plenty left": clamp for the 32-bit per-segment bookkeeping
 
+    // (row, t) = position of the current segment; advancing by `stride` segments is an add with carry,
+    // so the loop has no division
     unsigned seg = blockIdx.x * kWarps + warp;
-    long long row = 0, o0 = 0;
-    const char* xrow = nullptr;
-    int nch = 0;
-    // segment index -> row, first output, row base, number of 16-byte chunks to stage
-#define SG_LOCATE(seg_, row_, o0_, xrow_, nch_)                                                       \
-    do {                                                                                             \
-        unsigned r_ = (seg_), t_ = 0;                                                                \
-        if (spr != 1) { r_ = (seg_) / spr; t_ = (seg_) - r_ * spr; }                                 \
-        row_ = r_;                                                                                   \
-        o0_ = static_cast<long long>(t_) * kSeg;                                                     \
-        xrow_ = a.in + row_ * a.in_row_bytes;                                                        \
-        const long long left_ = len - o0_;                                                           \
-        nch_ = (static_cast<int>(left_ < kSeg ? left_ : kSeg) + 2 * N + DELTA + 3) >> 2;             \
-    } while (0)
+    unsigned row_u = seg / spr, t = seg - row_u * spr;
+    const unsigned step_r = stride / spr, step_t = stride - step_r * spr;
+    long long row = row_u;
+    float4* buf_cur = s_buf[warp][0];  // buffer holding (or receiving) the current segment
+    float4* buf_nxt = s_buf[warp][1];  // buffer the next segment is prefetched into
+    const int lane_chunk = lane + (lane >> 3);
 
+    long long o0 = static_cast<long long>(t) * kSeg;
+    const char* xrow = a.in + row * a.in_row_bytes;
     if (seg < nseg) {
-        SG_LOCATE(seg, row, o0, xrow, nch);
-        stage_segment<LEAD, N>(s_buf[warp][0], a, xrow, row, o0, nch, lane);
+        const long long l64 = len - o0;
+        stage_segment<LEAD, N>(buf_cur + lane_chunk, buf_cur, a, xrow, row, o0, static_cast<int>(l64 < kBig ? l64 : kBig), rows_aligned, lane);
     }
     cp_async_commit();
 
-    for (int it = 0; seg < nseg; ++it, seg += stride) {
-        // prefetch this warp's next segment into its other buffer
-        const unsigned nxt = seg + stride;
-        long long nrow = 0, no0 = 0;
-        const char* nxrow = nullptr;
-        int nnch = 0;
-        if (nxt < nseg) {
-            SG_LOCATE(nxt, nrow, no0, nxrow, nnch);
-            stage_segment<LEAD, N>(s_buf[warp][(it + 1) & 1], a, nxrow, nrow, no0, nnch, lane);
+    for (; seg < nseg; seg += stride) {
+        // position of this warp's next segment; prefetch it into the other buffer
+        unsigned nt = t + step_t;
+        long long nrow = row + step_r;
+        if (nt >= spr) { nt -= spr; ++nrow; }
+        const long long no0 = static_cast<long long>(nt) * kSeg;
+        const char* nxrow = a.in + nrow * a.in_row_bytes;
+        if (seg + stride < nseg) {
+            const long long l64 = len - no0;
+            stage_segment<LEAD, N>(buf_nxt + lane_chunk, buf_nxt, a, nxrow, nrow, no0,
+                                   static_cast<int>(l64 < kBig ? l64 : kBig), rows_aligned, lane);
         }
         cp_async_commit();
 
@@ -335,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, SG_MIN_BLOCKS) sg1d_kernel(const __g
         cp_async_wait<1>();  // this lane's copies of the current segment have landed ...
         __syncwarp();        // ... and so have the other lanes' (and their s_edge entries)
 
-        const float4* sb = s_buf[warp][it & 1] + 9 * lane;
+        const float4* sb = buf_cur + 9 * lane;
         float out[kR];
         if constexpr (ARITH == ARITH_FAST) compute_fast<N, DELTA>(sb, W, a.scale, out);
         else compute_exact<N, DELTA, ARITH>(sb, W, a.scale, out);
@@ -355,22 +360,39 @@ __global__ void __launch_bounds__(kThreads, SG_MIN_BLOCKS) sg1d_kernel(const __g
             for (int i = lane; i < a.state_w; i += 32)
                 a.state_out[row * a.state_pitch + i] = virtual_sample<LEAD, N>(a, xrow, row, len - a.state_w + i);
 
-        char* orow = a.out + row * a.out_row_bytes;
-        if (a.out_stride == 4 && o + kR <= a.out_len && ((reinterpret_cast<uintptr_t>(orow) + static_cast<uintptr_t>(o * 4)) & 15) == 0) {
-            float* dst = reinterpret_cast<float*>(orow) + o;
+        // Store through the warp's own buffer: each lane parks its 32 consecutive outputs (8 chunks at
+        // 9*lane, conflict free), then the warp writes the segment out in lane-interleaved order so that
+        // every store instruction covers one contiguous run of global memory (512 B when the row is
+        // 16-byte aligned, 128 B otherwise) instead of 32 scattered 16-byte pieces.
+        __syncwarp();  // every lane has finished reading its window (windows overlap between lanes)
+        {
+            float4* park = buf_cur + 9 * lane;
 #pragma unroll
-            for (int q = 0; q < kR / 4; ++q)
-                st_cs_f4(dst + 4 * q, make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]));
-        } else {
-#pragma unroll
-            for (int j = 0; j < kR; ++j)
-                if (o + j < a.out_len) *reinterpret_cast<float*>(orow + (o + j) * a.out_stride) = out[j];
+            for (int q = 0; q < kR / 4; ++q) park[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
         }
-        __syncwarp();  // all lanes are done with s_buf[warp][it&1] and s_edge[warp] before the refill
-        row = nrow; o0 = no0; xrow = nxrow; nch = nnch;
+        __syncwarp();
+        char* orow = a.out + row * a.out_row_bytes;
+        const long long remain = a.out_len - o0;  // outputs of this segment that may be stored
+        if (a.out_stride == 4 && remain >= kSeg && ((reinterpret_cast<uintptr_t>(orow) + static_cast<uintptr_t>(o0 * 4)) & 15) == 0) {
+            float* dst = reinterpret_cast<float*>(orow) + o0 + 4 * lane;
+            const float4* src = buf_cur + lane + (lane >> 3);
+#pragma unroll
+            for (int i = 0; i < kR / 4; ++i) st_cs_f4(dst + 128 * i, src[36 * i]);  // chunk lane + 32 i
+        } else {
+            const int lim = remain < kSeg ? static_cast<int>(remain) : kSeg;
+            const float* srcf = reinterpret_cast<const float*>(buf_cur);
+#pragma unroll 4
+            for (int i = 0; i < kR; ++i) {
+                const int f = 32 * i + lane;  // output index inside the segment; lives at chunk f/4 (+pad), word f%4
+                if (f < lim)
+                    *reinterpret_cast<float*>(orow + (o0 + f) * a.out_stride) = srcf[4 * ((f >> 2) + (f >> 5)) + (f & 3)];
+            }
+        }
+        __syncwarp();  // all lanes are done with buf_cur and s_edge[warp] before the refill
+        row = nrow; o0 = no0; xrow = nxrow; t = nt;
+        float4* const tmp = buf_cur; buf_cur = buf_nxt; buf_nxt = tmp;
     }
     cp_async_wait<0>();
-#undef SG_LOCATE
 }
 
 }  // namespace sg

@@ -10,6 +10,7 @@ namespace sg {
 constexpr int kThreads = 128;              // 4 warps per CTA
 constexpr int kR = 32;                     // consecutive outputs per thread (register sliding window)
 constexpr int kTile = 32 * kR;             // 1024 outputs per segment (one warp)
+constexpr int kSeg = kTile;
 constexpr int kMaxN = 32;
 constexpr int kMaxWs = 2 * kMaxN + 1;      // 65, ref: include/iterative/savgolFilter.h:42
 
