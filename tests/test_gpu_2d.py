@@ -1,0 +1,134 @@
+"""GPU parity tests of the 2D path (savgol2d_* through the C ABI) vs the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+import savgol_b200 as sg  # noqa: E402
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.fixture(autouse=True)
+def _fast_mode():
+    sg.set_exact(False)
+    yield
+    sg.set_exact(False)
+
+
+CASES = [(1, 1, 1, 0, 0), (2, 2, 2, 0, 0), (2, 2, 2, 1, 0), (2, 1, 2, 0, 1), (3, 4, 4, 1, 1), (7, 7, 3, 0, 0), (7, 7, 3, 2, 0),
+         (5, 3, 6, 2, 2), (16, 16, 6, 0, 0), (4, 4, 3, 0, 0), (8, 8, 2, 0, 2), (12, 12, 5, 1, 0)]
+
+
+@pytest.mark.parametrize("nx,ny,order,dx,dy", CASES)
+def test_apply_all_boundaries(oracle, nx, ny, order, dx, dy):
+    rng = np.random.default_rng(nx * 1000 + ny * 100 + order * 10 + dx + dy)
+    hx, hy = 0.5, 2.0
+    o = oracle.Filter2D(nx, ny, order, dx, dy, hx, hy)
+    f = sg.Savgol2DFilter(nx, ny, order, dx, dy, hx, hy)
+    for rows, cols in ((2 * ny + 1, 2 * nx + 1), (2 * ny + 2, 2 * nx + 5), (97, 131), (260, 300)):
+        img = rng.standard_normal((rows, cols)).astype(np.float32)
+        d_img = torch.from_numpy(img).cuda()
+        tol = 1e-6 * float(np.abs(img).max()) * o.scale * 1.0
+        for b in ("valid", "constant", "reflect"):
+            ref = np.full(img.shape, -3.0, np.float32)
+            o.apply(img, b, ref)
+            out = torch.full(img.shape, -3.0, device="cuda")
+            f.apply(d_img, b, out=out)
+            got = out.cpu().numpy()
+            assert np.max(np.abs(got - ref)) <= tol, (rows, cols, b, float(np.max(np.abs(got - ref))), tol)
+            if b == "valid":   # border untouched (ref: include/iterative/savgol2d.h:108-112)
+                assert np.all(got[:ny] == -3.0) and np.all(got[:, :nx] == -3.0)
+            sg.set_exact(True)
+            out.fill_(-3.0)
+            f.apply(d_img, b, out=out)
+            sg.set_exact(False)
+            assert np.array_equal(bits(out.cpu().numpy()), bits(ref)), (rows, cols, b)
+        v = f.apply_valid(d_img).cpu().numpy()
+        assert np.max(np.abs(v - o.apply_valid(img))) <= tol
+
+
+def test_golden_reference_outputs_exact(golden_dir):
+    G = np.load(os.path.join(golden_dir, "ref_outputs.npz"))
+    sg.set_exact(True)
+    for ci, (nx, ny, o, dx, dy) in enumerate(G["cases2d"]):
+        f = sg.Savgol2DFilter(int(nx), int(ny), int(o), int(dx), int(dy), 0.5, 2.0)
+        img = torch.from_numpy(G[f"d{ci}_img"]).cuda()
+        for b in range(3):
+            out = torch.full(img.shape, -3.0, device="cuda")
+            f.apply(img, b, out=out)
+            assert np.array_equal(bits(out.cpu().numpy()), bits(G[f"d{ci}_apply_b{b}"])), (ci, b)
+
+
+def test_config4_window_batch_constant(oracle):
+    # BASELINE config 4 filter (15x15, order 3, constant) on a small batch of images, strided views
+    rng = np.random.default_rng(3)
+    f = sg.Savgol2DFilter(7, 7, 3)
+    o = oracle.Filter2D(7, 7, 3)
+    big = torch.from_numpy(rng.random((3, 200, 340)).astype(np.float32)).cuda()
+    view = big[:, 10:190, 20:320]          # in_stride 340, image pitch 200*340
+    out = torch.zeros(3, 180, 300, device="cuda")
+    f.apply(view, "constant", out=out)
+    for i in range(3):
+        ref = o.apply(view[i].cpu().numpy().copy(), "constant")
+        assert np.max(np.abs(out[i].cpu().numpy() - ref)) <= 1e-6
+    # host path == device path
+    h = f.apply(view[0].cpu().numpy().copy(), "constant")
+    assert np.array_equal(bits(h), bits(out[0].cpu().numpy()))
+
+
+def test_reference_properties():
+    # ref: test/iterative/test_savgol2d.c:126-356 -- constant / plane preserved, derivatives of polynomials
+    yy, xx = np.mgrid[0:40, 0:50].astype(np.float32)
+    const = np.full((20, 20), 42.0, np.float32)
+    f = sg.Savgol2DFilter(2, 2, 2)
+    assert np.allclose(f.apply(torch.from_numpy(const).cuda(), "constant").cpu().numpy(), 42.0, atol=1e-3)
+    plane = (2 * xx + 3 * yy).astype(np.float32)
+    v = f.apply_valid(torch.from_numpy(plane).cuda()).cpu().numpy()
+    assert np.allclose(v, plane[2:-2, 2:-2], atol=1e-2)
+    for (dx, dy, img, want) in [(1, 0, 5 * xx, 5.0), (0, 1, 7 * yy, 7.0), (2, 0, xx * xx, 2.0), (0, 2, 3 * yy * yy, 6.0),
+                                (1, 1, 4 * xx * yy, 4.0)]:
+        g = sg.Savgol2DFilter(3, 3, 3, dx, dy).apply_valid(torch.from_numpy(img.astype(np.float32)).cuda()).cpu().numpy()
+        assert np.allclose(g, want, atol=2e-2), (dx, dy)
+    # rectangular window (ref :508-543)
+    r = sg.Savgol2DFilter(2, 1, 2).apply(torch.from_numpy(const).cuda(), "constant").cpu().numpy()
+    assert np.allclose(r, 42.0, atol=1e-3)
+
+
+def test_wrappers_vs_oracle_composition(oracle):
+    # ref: src/savgol2d.c:462-618 -- gradient / hessian / laplacian are compositions of single filters
+    rng = np.random.default_rng(8)
+    img = rng.standard_normal((64, 80)).astype(np.float32)
+    d = torch.from_numpy(img).cuda()
+    gx, gy = sg.gradient(d, 3, 3, 3, 0.5, 2.0, "constant")
+    hxx, hxy, hyy = sg.hessian(d, 3, 3, 3, 0.5, 2.0, "reflect")
+    lap = sg.laplacian(d, 3, 3, 3, 0.5, 2.0, "constant")
+
+    def ref(dx, dy, b):
+        return oracle.Filter2D(3, 3, 3, dx, dy, 0.5, 2.0).apply(img, b)
+    s = float(np.abs(img).max())
+    assert np.max(np.abs(gx.cpu().numpy() - ref(1, 0, "constant"))) <= 1e-6 * s * 2
+    assert np.max(np.abs(gy.cpu().numpy() - ref(0, 1, "constant"))) <= 1e-6 * s
+    assert np.max(np.abs(hxx.cpu().numpy() - ref(2, 0, "reflect"))) <= 1e-6 * s * 4
+    assert np.max(np.abs(hxy.cpu().numpy() - ref(1, 1, "reflect"))) <= 1e-6 * s
+    assert np.max(np.abs(hyy.cpu().numpy() - ref(0, 2, "reflect"))) <= 1e-6 * s
+    want = ref(2, 0, "constant") + ref(0, 2, "constant")
+    assert np.max(np.abs(lap.cpu().numpy() - want)) <= 1e-6 * s * 4.5
+    # host-pointer wrappers give the same numbers
+    lap_h = sg.laplacian(img.copy(), 3, 3, 3, 0.5, 2.0, "constant")
+    assert np.max(np.abs(lap_h - lap.cpu().numpy())) <= 1e-7 * s * 4.5
+    with pytest.raises(RuntimeError):
+        sg.laplacian(d, 3, 3, 1)
+
+
+def test_errors_like_reference():
+    f = sg.Savgol2DFilter(3, 3, 2)
+    lib = sg.lib()
+    x = torch.zeros(5, 5, device="cuda")
+    assert lib.savgol2d_apply_valid(f.handle, x.data_ptr(), 5, 5, 5, x.data_ptr(), 5) == -1   # ref: src/savgol2d.c:371
+    assert lib.savgol2d_apply(f.handle, None, 5, 5, 5, x.data_ptr(), 5, 1) == -1
+    assert lib.savgol2d_apply(f.handle, x.data_ptr(), 5, 5, 5, x.data_ptr(), 5, 0) == -1
