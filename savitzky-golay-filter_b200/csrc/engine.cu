@@ -149,6 +149,14 @@ bool run1d_device(const Problem1D& p, cudaStream_t stream)
     sg::W1D w;
     std::memset(&w, 0, sizeof(w));
     std::memcpy(w.w, f->center_weights, sizeof(float) * static_cast<size_t>(2 * n + 1));
+    {
+        // FAST flavour: weights pre-scaled by 1/dt^d and paired (see sg_common.cuh)
+        const float sc = (f->dt_scale != 0.0f) ? (1.0f / f->dt_scale) : 1.0f;
+        const int ws = 2 * n + 1;
+        w.ws_first = f->center_weights[0] * sc;
+        w.ws_last = f->center_weights[ws - 1] * sc;
+        for (int k = 1; k < ws; ++k) w.pw[k] = make_float2(f->center_weights[k] * sc, f->center_weights[k - 1] * sc);
+    }
 
     sg::Args1D a;
     std::memset(&a, 0, sizeof(a));

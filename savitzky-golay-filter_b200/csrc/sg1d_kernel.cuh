@@ -153,45 +153,44 @@ __device__ __forceinline__ void stage_segment(float4* dst0 /* buf + lane + (lane
 }
 
 // ---------------------------------------------------------------------------------------------
-// FAST arithmetic: packed FFMA2, parity-split accumulators.
+// FAST arithmetic: packed FFMA2 over output pairs.
+// acc[jj] = (out[2jj], out[2jj+1]).  Sample x[i] (window position i of this thread) is tap k = i-2jj-DELTA
+// of out[2jj] and tap k-1 of out[2jj+1], so   acc[jj] += (ws[k], ws[k-1]) * (x, x)   is one FFMA2 with
+// the sample broadcast and the weight pair taken from uniform registers.  The first / last tap of a
+// pair touch only one of its outputs and are scalar FFMAs.  Pipe work per thread: 32 x (2n+1) MACs,
+// exactly the stencil's minimum; weights are pre-scaled by 1/dt^d, so there is no epilogue.
 template <int N, int DELTA>
-__device__ __forceinline__ void compute_fast(const float4* __restrict__ sb, const W1D& W, float scale, float (&out)[kR])
+__device__ __forceinline__ void compute_fast(const float4* __restrict__ sb, const W1D& W, float (&out)[kR])
 {
     constexpr int WS = 2 * N + 1;
     constexpr int NCHT = (kR + 2 * N + DELTA + 3) / 4;
-    float2 Pe[kR / 2];      // Pe[jj] = partial (out[2jj],   out[2jj+1]) : taps with k+DELTA even
-    float2 Po[kR / 2 + 1];  // Po[jj] = partial (out[2jj-1], out[2jj])   : taps with k+DELTA odd
+    float2 acc[kR / 2];
 #pragma unroll
-    for (int i = 0; i < kR / 2; ++i) Pe[i] = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < kR / 2 + 1; ++i) Po[i] = make_float2(0.f, 0.f);
+    for (int i = 0; i < kR / 2; ++i) acc[i] = make_float2(0.f, 0.f);
 
-    // static_for: the window is up to 24 chunks x 66 FFMA2; "#pragma unroll" silently gives up on
-    // bodies that large (half-windows > 20), and a rolled loop would index weights and accumulators
-    // dynamically.  Template expansion keeps every index a compile-time constant.
+    // static_for: the window is up to 24 chunks x 68 FMA instructions; "#pragma unroll" silently gives
+    // up on bodies that large (half-windows > 20), and a rolled loop would index weights and
+    // accumulators dynamically.  Template expansion keeps every index a compile-time constant.
     static_for<NCHT>([&](auto ci) {
         constexpr int c = decltype(ci)::value;
         const float4 v = sb[c + (c >> 3)];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int s = 4 * c + 2 * h;  // shared sample index of this aligned pair
-            const float2 X = h == 0 ? make_float2(v.x, v.y) : make_float2(v.z, v.w);
+        for (int e = 0; e < 4; ++e) {
+            const int i = 4 * c + e;
+            const float x = e == 0 ? v.x : e == 1 ? v.y : e == 2 ? v.z : v.w;
 #pragma unroll
             for (int jj = 0; jj < kR / 2; ++jj) {
-                const int k = s - 2 * jj - DELTA;
-                if (k >= 0 && k < WS) Pe[jj] = __ffma2_rn(make_float2(W.w[k], W.w[k]), X, Pe[jj]);
-            }
-#pragma unroll
-            for (int jj = 0; jj < kR / 2 + 1; ++jj) {
-                const int k = s - (2 * jj - 1) - DELTA;
-                if (k >= 0 && k < WS) Po[jj] = __ffma2_rn(make_float2(W.w[k], W.w[k]), X, Po[jj]);
+                const int k = i - 2 * jj - DELTA;  // tap of out[2jj]; out[2jj+1] sees tap k-1
+                if (k == 0) acc[jj].x = fmaf(W.ws_first, x, acc[jj].x);
+                else if (k == WS) acc[jj].y = fmaf(W.ws_last, x, acc[jj].y);
+                else if (k > 0 && k < WS) acc[jj] = __ffma2_rn(W.pw[k], make_float2(x, x), acc[jj]);
             }
         }
     });
 #pragma unroll
     for (int jj = 0; jj < kR / 2; ++jj) {
-        out[2 * jj] = (Pe[jj].x + Po[jj].y) * scale;
-        out[2 * jj + 1] = (Pe[jj].y + Po[jj + 1].x) * scale;
+        out[2 * jj] = acc[jj].x;
+        out[2 * jj + 1] = acc[jj].y;
     }
 }
 
@@ -342,7 +341,7 @@ __global__ void __launch_bounds__(kThreads, SG_MIN_BLOCKS) sg1d_kernel(const __g
 
         const float4* sb = buf_cur + 9 * lane;
         float out[kR];
-        if constexpr (ARITH == ARITH_FAST) compute_fast<N, DELTA>(sb, W, a.scale, out);
+        if constexpr (ARITH == ARITH_FAST) compute_fast<N, DELTA>(sb, W, out);
         else compute_exact<N, DELTA, ARITH>(sb, W, a.scale, out);
 
         const long long o = o0 + kR * lane;
@@ -356,9 +355,24 @@ __global__ void __launch_bounds__(kThreads, SG_MIN_BLOCKS) sg1d_kernel(const __g
         }
 
         // stream: hand the last state_w samples of [lead pad | x] to the next chunk
-        if (a.state_out != nullptr && o0 + kSeg >= len)
-            for (int i = lane; i < a.state_w; i += 32)
-                a.state_out[row * a.state_pitch + i] = virtual_sample<LEAD, N>(a, xrow, row, len - a.state_w + i);
+        // (read back from the staged segment whenever it holds them: a global re-read would put a
+        // full L2 round trip on every segment's critical path)
+        if (a.state_out != nullptr && o0 + kSeg >= len) {
+            constexpr int PAD = Geo<LEAD>::PAD;
+            const long long first = len - a.state_w;         // x index of the oldest carried sample
+            const bool staged = first >= o0 - PAD;
+            const float* bf = reinterpret_cast<const float*>(buf_cur);
+            for (int i = lane; i < a.state_w; i += 32) {
+                float v;
+                if (staged) {
+                    const int pos = static_cast<int>(first - (o0 - PAD)) + i;  // sample position in the buffer
+                    v = bf[4 * ((pos >> 2) + (pos >> 5)) + (pos & 3)];
+                } else {
+                    v = virtual_sample<LEAD, N>(a, xrow, row, first + i);
+                }
+                a.state_out[row * a.state_pitch + i] = v;
+            }
+        }
 
         // Store through the warp's own buffer: each lane parks its 32 consecutive outputs (8 chunks at
         // 9*lane, conflict free), then the warp writes the segment out in lane-interleaved order so that

@@ -23,9 +23,19 @@ enum : int { MODE_POLY = 0, MODE_REFLECT = 1, MODE_PERIODIC = 2, MODE_CONSTANT =
 //         to the stream API.
 enum : int { ARITH_FAST = 0, ARITH_EXACT4 = 1, ARITH_EXACTSEQ = 2 };
 
-// Centre weights travel as a kernel parameter: they land in constant bank 0 and ptxas keeps
-// them in uniform registers, so every FFMA2 takes its weight as a UR operand.
-struct W1D { float w[kMaxWs]; };
+// Centre weights travel as a kernel parameter: they land in constant bank 0 and ptxas feeds them
+// to the FMA pipe as uniform-register operands.
+//   w[k]    : the reference's centre weights (exact flavours; polynomial edges use their own table)
+//   pw[k]   : FAST flavour, pair (ws[k], ws[k-1]) with ws = w * (1/dt^d) pre-scaled on the host, k = 1..2n:
+//             one sample x[i] updates two neighbouring outputs (out[j] by tap k, out[j+1] by tap k-1)
+//             with a single packed FFMA2, the sample broadcast to both halves.
+//   ws_first / ws_last : scaled w[0] and w[2n] for the two half-pairs at the window ends (scalar FFMA,
+//             so no sample outside an output's true window is ever multiplied, not even by zero).
+struct W1D {
+    float w[kMaxWs];
+    float ws_first, ws_last, pad_;
+    float2 pw[kMaxWs + 1];
+};
 
 // One launch = `rows` independent signals of `len` samples, cut into tiles of kTile outputs.
 // Virtual signal V per row:  V = [ lead pad | x[0..len) | n pad ],  out[o] = scale * sum_k w[k] V[o+k],
