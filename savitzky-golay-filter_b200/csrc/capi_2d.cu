@@ -84,8 +84,7 @@ bool run2d_device(const Savgol2DFilter* f, const float* in, int rows, int cols, 
     }
     const bool exact = sge::exact_mode() != 0;
     Filter2DImpl* fi = live2d(f);
-    if (!exact && fi && fi->plan.rank > 0) {
-        // in-place is not supported by the tiled kernels; go through scratch like the 1D path
+    if (!exact && fi && sg2d::separable_supported(a, fi->plan)) {
         return cuda_ok(sg2d::launch_separable(a, fi->plan, st), "sg2d separable launch");
     }
     float* temp = nullptr;

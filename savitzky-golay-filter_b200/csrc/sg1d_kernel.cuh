@@ -29,7 +29,7 @@
 #include "sg_common.cuh"
 
 #ifndef SG_MIN_BLOCKS
-#define SG_MIN_BLOCKS 4  // resident CTAs per SM the register allocator must allow
+#define SG_MIN_BLOCKS 5  // resident CTAs per SM the register allocator must allow
 #endif
 
 namespace sg {

@@ -38,8 +38,11 @@ struct SepPlan {
     float row[kMaxRank][33];  // row[r][x + nx]
     float col[kMaxRank][33];  // col[r][y + ny]
     float max_err;            // max |W - sum_r col*row| / max|W|
+    float sum_err;            // sum |W - sum_r col*row|  (bounds the extra output error per unit max|image|)
+    int parity_x, parity_y;   // +1: factors even in x / y, -1: odd
 };
 void plan_separable(int nx, int ny, int order, const double* coef, const float* weights, SepPlan* plan);
+bool separable_supported(const Args2D& a, const SepPlan& plan);
 cudaError_t launch_separable(const Args2D& a, const SepPlan& plan, cudaStream_t stream);
 
 }  // namespace sg2d

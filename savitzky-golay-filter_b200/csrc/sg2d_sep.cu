@@ -1,17 +1,290 @@
-// sg2d_sep.cu -- separable fast path of the 2D filter (placeholder: planning disabled until the
-// tiled kernel lands; every filter currently runs through sg2d_direct.cu).
+// sg2d_sep.cu -- production path of the 2D filter: streaming separable stencil for sm_100a.
+//
+// Replaces the reference's 4-deep tap loop (src/savgol2d.c:417-452, 374-393).  The weight table is
+// factorised on the host as W[y][x] = sum_{r<R} col_r[y] * row_r[x] (factor2d.cpp, R <= 4, R = 2 for
+// the order-2/3 smoothing filters), all row factors even or all odd in x.
+//
+// Execution plan -- warp-autonomous, like the 1D kernel; no __syncthreads anywhere:
+//   * work item = (image, band of 512 output rows, strip of 32*RX output columns); a warp walks DOWN
+//     its strip one input row per step.  Rows are staged by cp.async into a private ring of 8 row
+//     buffers, 6 rows ahead of the row being consumed (~3.4 KB in flight per warp); the row index is
+//     mapped by the boundary rule (clamp / half-sample reflect), the few pad columns of the first /
+//     last strip go through a per-element edge path, so the compute is boundary agnostic.
+//   * ROW PASS: each lane owns RX consecutive columns; from a register window of the staged row it
+//     forms the folded sums s_k = x[c+k] +/- x[c-k] once and evaluates the R row factors on them
+//     (n adds + R*(n+1) FMAs per pixel instead of R*(2n+1) MACs).
+//   * COLUMN PASS, in registers: the lane keeps the 2n+1 partially accumulated output rows of its
+//     columns.  The R values just produced are scattered into them with packed FFMA2 (value broadcast,
+//     weight pair (col[k], col[k-1]) from uniform registers, output rows paired), the oldest row
+//     is complete and is stored (one 512-byte store per warp and row).  Accumulator indices are
+//     static inside blocks of U = 4 rows; a block ends with a register shift.
+//   => every input pixel is read from HBM once and from shared memory (RX+2n)/RX times, no
+//      intermediate image ever exists, and there is no vertical halo recomputation except the 2n
+//      warm-up rows per band.
+#include <atomic>
+
 #include "sg2d.h"
+#include "sg_common.cuh"
+
+namespace sg { extern std::atomic<unsigned long long> g_launches; }
 
 namespace sg2d {
 
-void plan_separable(int nx, int ny, int, const double*, const float*, SepPlan* plan)
+namespace {
+
+using sg::cp_async16;
+using sg::cp_async4;
+using sg::cp_async_commit;
+using sg::cp_async_wait;
+
+constexpr int kU = 4;         // rows per statically indexed block
+constexpr int kRing = 8;      // staged rows per warp
+constexpr int kAhead = 6;     // prefetch distance in rows (kRing >= kAhead + 2)
+constexpr int kBand = 512;    // output rows per work item
+constexpr int kWarps = 4;
+
+template <int R>
+struct SepW {
+    float rc[R];            // row factor, centre tap
+    float rk[R][16];        // rk[r][k-1]: weight of s_k = x[c+k] + sx * x[c-k], k = 1..n
+    float col[R][33];       // column factor * scale, col[r][wy], wy = 0..2n
+    float sx;               // +1 (even in x) / -1 (odd in x)
+};
+
+__device__ __forceinline__ int map_index(int i, int n, int boundary)
 {
-    plan->rank = 0;
-    plan->nx = nx;
-    plan->ny = ny;
-    plan->max_err = 0.0f;
+    if (boundary == B_REFLECT) {
+        if (i < 0) i = -i - 1;
+        else if (i >= n) i = 2 * n - i - 1;
+    }
+    if (i < 0) i = 0;
+    else if (i >= n) i = n - 1;
+    return i;
 }
 
-cudaError_t launch_separable(const Args2D&, const SepPlan&, cudaStream_t) { return cudaErrorNotSupported; }
+template <int N, int R, int RX>
+__global__ void __launch_bounds__(kWarps * 32, RX == 4 ? 4 : 3) sep_kernel(const __grid_constant__ SepW<R> w,
+                                                                            const __grid_constant__ Args2D a)
+{
+    constexpr int TW = 32 * RX;                 // output columns per strip
+    constexpr int PADX = (N + 3) & ~3;          // staged row starts PADX columns left of the strip (16 B aligned)
+    constexpr int DX = PADX - N;
+    constexpr int ROWF = TW + 2 * PADX;         // floats per staged row
+    constexpr int ROWCH = ROWF / 4;             // 16-byte chunks per staged row
+    constexpr int NA = 2 * N + kU;              // output rows in flight per column (block-static window)
+    constexpr int WIN = RX + DX + 2 * N;        // floats of the row window a lane touches
+    constexpr int VW = RX == 4 ? 4 : 2;         // floats per shared load
+    constexpr int NV = (WIN + VW - 1) / VW;
+
+    __shared__ __align__(16) float s_ring[kWarps][kRing][ROWF];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float(*ring)[ROWF] = s_ring[warp];
+
+    const int Ylo = a.cy, Yhi = a.cy + a.out_rows;      // stored region in full-image coordinates
+    const int Xlo = a.cx, Xhi = a.cx + a.out_cols;
+    const int strips = (Xhi + TW - 1) / TW;
+    const int bands = (a.out_rows + kBand - 1) / kBand;
+    const long long per_img = static_cast<long long>(strips) * bands;
+    const long long items = per_img * a.n_images;
+    const long long nwarps = static_cast<long long>(gridDim.x) * kWarps;
+
+    for (long long item = static_cast<long long>(blockIdx.x) * kWarps + warp; item < items; item += nwarps) {
+        const long long img = item / per_img;
+        const int rem = static_cast<int>(item - img * per_img);
+        const int band = rem / strips, strip = rem - band * strips;
+        const int x0 = strip * TW;
+        if (x0 + TW <= Xlo) continue;                   // strip entirely left of the stored region (VALID)
+        const int Y0 = Ylo + band * kBand;
+        const int nrows = min(kBand, Yhi - Y0);
+        const int steps = nrows + 2 * N;
+        const float* in = a.in + img * a.in_image_pitch;
+        // virtual output base: element (Y, X) of the full-size result lives at vout + Y*os + X
+        float* vout = a.out + img * a.out_image_pitch - static_cast<long long>(a.cy) * a.out_stride - a.cx;
+
+        // ---- staging of input row `t` of this band (centre row Y0 - N + t) ----
+        auto stage_row = [&](int t) {
+            const int iy = map_index(Y0 - N + t, a.rows, a.boundary);
+            const float* src = in + static_cast<long long>(iy) * a.in_stride;
+            float* dst = ring[t & (kRing - 1)];
+            const int xb = x0 - PADX;
+#pragma unroll
+            for (int c = lane; c < ROWCH; c += 32) {
+                const int xin = xb + 4 * c;
+                if (xin >= 0 && xin + 3 < a.cols) {
+                    cp_async16(dst + 4 * c, src + xin);
+                } else {
+#pragma unroll 1
+                    for (int e = 0; e < 4; ++e) cp_async4(dst + 4 * c + e, src + map_index(xin + e, a.cols, a.boundary));
+                }
+            }
+        };
+
+        __syncwarp();  // the previous item's last reads of the ring are done
+#pragma unroll 1
+        for (int t = 0; t < kAhead; ++t) {
+            if (t < steps) stage_row(t);
+            cp_async_commit();
+        }
+
+        // acc[jp][i]: output row (block base - 2n + i) of the column pair (2jp, 2jp+1) of this lane
+        float2 acc[RX / 2][NA];
+#pragma unroll
+        for (int jp = 0; jp < RX / 2; ++jp)
+#pragma unroll
+            for (int i = 0; i < NA; ++i) acc[jp][i] = make_float2(0.f, 0.f);
+
+#pragma unroll 1
+        for (int tb = 0; tb * kU < steps; ++tb) {
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int t = tb * kU + u;
+                if (t < steps) {
+                    if (t + kAhead < steps) stage_row(t + kAhead);
+                    cp_async_commit();
+                    cp_async_wait<kAhead>();   // row t has landed (this lane's part) ...
+                    __syncwarp();              // ... and everybody else's
+
+                    // ---- row pass ----
+                    float xs[NV * VW];
+                    const float* rowp = ring[t & (kRing - 1)] + RX * lane;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        if constexpr (VW == 4) {
+                            const float4 q = *reinterpret_cast<const float4*>(rowp + 4 * v);
+                            xs[4 * v] = q.x; xs[4 * v + 1] = q.y; xs[4 * v + 2] = q.z; xs[4 * v + 3] = q.w;
+                        } else {
+                            const float2 q = *reinterpret_cast<const float2*>(rowp + 2 * v);
+                            xs[2 * v] = q.x; xs[2 * v + 1] = q.y;
+                        }
+                    }
+                    // folded sums s_k = x[c+k] +/- x[c-k] are shared by the R row factors; the weighted
+                    // sums run packed over column pairs (weight broadcast)
+                    float2 hp[R][RX / 2];
+#pragma unroll
+                    for (int jp = 0; jp < RX / 2; ++jp) {
+                        const int c0 = 2 * jp + DX + N;
+                        const float2 ctr = make_float2(xs[c0], xs[c0 + 1]);
+#pragma unroll
+                        for (int r = 0; r < R; ++r) hp[r][jp] = __fmul2_rn(make_float2(w.rc[r], w.rc[r]), ctr);
+#pragma unroll
+                        for (int k = 1; k <= N; ++k) {
+                            const float2 sk = make_float2(fmaf(w.sx, xs[c0 - k], xs[c0 + k]),      // +/-1 multiply is exact
+                                                          fmaf(w.sx, xs[c0 + 1 - k], xs[c0 + 1 + k]));
+#pragma unroll
+                            for (int r = 0; r < R; ++r)
+                                hp[r][jp] = __ffma2_rn(make_float2(w.rk[r][k - 1], w.rk[r][k - 1]), sk, hp[r][jp]);
+                        }
+                    }
+
+                    // ---- column pass: scatter the new row into the 2n+1 output rows in flight ----
+                    // output row i of the block window sees this input row as window row wy = u + 2n - i
+#pragma unroll
+                    for (int jp = 0; jp < RX / 2; ++jp)
+#pragma unroll
+                        for (int r = 0; r < R; ++r)
+#pragma unroll
+                            for (int i = u; i <= u + 2 * N; ++i) {
+                                const float cw = w.col[r][u + 2 * N - i];
+                                acc[jp][i] = __ffma2_rn(make_float2(cw, cw), hp[r][jp], acc[jp][i]);
+                            }
+
+                    // ---- the oldest output row (index u of the block) is complete ----
+                    if (t >= 2 * N) {
+                        const int Y = Y0 + t - 2 * N;
+                        const int X = x0 + RX * lane;
+                        float o[RX];
+#pragma unroll
+                        for (int jp = 0; jp < RX / 2; ++jp) { o[2 * jp] = acc[jp][u].x; o[2 * jp + 1] = acc[jp][u].y; }
+                        float* dst = vout + static_cast<long long>(Y) * a.out_stride + X;
+                        if (X >= Xlo && X + RX <= Xhi && (reinterpret_cast<uintptr_t>(dst) & (4 * RX - 1)) == 0) {
+                            if constexpr (RX == 4) sg::st_cs_f4(dst, make_float4(o[0], o[1], o[2], o[3]));
+                            else *reinterpret_cast<float2*>(dst) = make_float2(o[0], o[1]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < RX; ++j)
+                                if (X + j >= Xlo && X + j < Xhi) dst[j] = o[j];
+                        }
+                    }
+                }
+            }
+            // block done: drop the kU completed rows
+#pragma unroll
+            for (int jp = 0; jp < RX / 2; ++jp)
+#pragma unroll
+                for (int i = 0; i < NA; ++i) acc[jp][i] = (i + kU < NA) ? acc[jp][i + kU] : make_float2(0.f, 0.f);
+        }
+        cp_async_wait<0>();
+    }
+}
+
+template <int N, int R>
+cudaError_t launch_nr(const Args2D& a, const SepPlan& plan, cudaStream_t stream)
+{
+    constexpr int RX = N <= 8 ? 4 : 2;
+    SepW<R> w;
+    const float sc = a.scale;
+    for (int r = 0; r < R; ++r) {
+        w.rc[r] = plan.row[r][N];
+        for (int k = 1; k <= N; ++k) w.rk[r][k - 1] = plan.row[r][N + k];
+        for (int k = 0; k <= 2 * N; ++k) w.col[r][k] = plan.col[r][k] * sc;
+    }
+    w.sx = plan.parity_x < 0 ? -1.0f : 1.0f;
+    auto kern = sep_kernel<N, R, RX>;
+    static int bps = 0, sms = 0;
+    if (bps == 0) {
+        int dev = 0, nb = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kWarps * 32, 0);
+        if (e != cudaSuccess) return e;
+        bps = nb > 0 ? nb : 1;
+    }
+    constexpr int TW = 32 * RX;
+    const long long strips = (a.cx + a.out_cols + TW - 1) / TW, bands = (a.out_rows + kBand - 1) / kBand;
+    const long long items = strips * bands * a.n_images;
+    if (items <= 0) return cudaSuccess;
+    long long grid = static_cast<long long>(sms) * bps;
+    const long long need = (items + kWarps - 1) / kWarps;
+    if (grid > need) grid = need;
+    kern<<<static_cast<unsigned>(grid), kWarps * 32, 0, stream>>>(w, a);
+    sg::g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+template <int N>
+cudaError_t launch_n(const Args2D& a, const SepPlan& plan, cudaStream_t stream)
+{
+    switch (plan.rank) {
+        case 1: return launch_nr<N, 1>(a, plan, stream);
+        case 2: return launch_nr<N, 2>(a, plan, stream);
+        case 3: return launch_nr<N, 3>(a, plan, stream);
+        case 4: return launch_nr<N, 4>(a, plan, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace
+
+// The streaming kernel is instantiated for square windows (nx == ny); it needs 16-byte aligned
+// rows on both sides.  Everything else runs through sg2d_direct.cu.
+bool separable_supported(const Args2D& a, const SepPlan& plan)
+{
+    if (plan.rank < 1 || plan.rank > kMaxRank || plan.nx != plan.ny) return false;
+    if ((reinterpret_cast<uintptr_t>(a.in) & 15) || (a.in_stride & 3) || (a.in_image_pitch & 3)) return false;
+    if (a.rows < 1 || a.cols < 4) return false;
+    return true;
+}
+
+cudaError_t launch_separable(const Args2D& a, const SepPlan& plan, cudaStream_t stream)
+{
+    switch (plan.nx) {
+#define SG2D_CASE(n) case n: return launch_n<n>(a, plan, stream);
+        SG2D_CASE(1) SG2D_CASE(2) SG2D_CASE(3) SG2D_CASE(4) SG2D_CASE(5) SG2D_CASE(6) SG2D_CASE(7) SG2D_CASE(8)
+        SG2D_CASE(9) SG2D_CASE(10) SG2D_CASE(11) SG2D_CASE(12) SG2D_CASE(13) SG2D_CASE(14) SG2D_CASE(15) SG2D_CASE(16)
+#undef SG2D_CASE
+        default: return cudaErrorInvalidValue;
+    }
+}
 
 }  // namespace sg2d
