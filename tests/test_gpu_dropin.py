@@ -1,0 +1,34 @@
+"""Drop-in acceptance: the reference's own test programs (test/iterative/*.c, public API only),
+compiled UNMODIFIED against include/ and linked against libsavgol_b200.so instead of the reference
+library (oracle/Makefile target `dropin`, built where /root/reference exists; the binaries travel in
+oracle/_ref/).  Every one of the reference's 71 checks must pass with the CUDA library underneath."""
+import os
+import re
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "oracle", "_ref")
+
+
+@pytest.mark.parametrize("name,min_pass", [("test_savgol_b200", 25), ("test_savgol_stream_b200", 19), ("test_savgol2d_b200", 27)])
+def test_reference_test_program_passes_on_our_library(name, min_pass):
+    exe = os.path.join(BIN, name)
+    if not os.path.exists(exe):
+        pytest.skip("drop-in binaries not built (make -C oracle dropin)")
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    out = p.stdout
+    assert p.returncode == 0, out[-2000:] + p.stderr[-2000:]
+    assert "[FAIL]" not in out, out[-2000:]
+    assert out.count("[PASS]") >= min_pass, out[-2000:]
+
+
+def test_reference_demo_program_runs():
+    exe = os.path.join(BIN, "test_savgol_main_b200")
+    if not os.path.exists(exe):
+        pytest.skip("drop-in binaries not built")
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0
+    assert re.search(r"Verification: PASS \(0 mismatches\)", p.stdout), p.stdout[-1500:]
