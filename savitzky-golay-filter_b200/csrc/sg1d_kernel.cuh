@@ -4,24 +4,24 @@
 // :547-580, the padded edges :785-801 / :442-535, the polynomial edges :769-784, VALID
 // :821-850, strided :877-934) and the steady-state of the stream (src/savgol_stream.c:224-226).
 //
-// Execution plan (one persistent CTA of 128 threads per resident slot, looping over tiles of
-// 4096 outputs of one signal):
-//   * cp.async (16 B, L2-only) stages tile+halo into shared memory, double buffered, so the next
-//     tile's HBM reads are in flight while the current tile is computed.  The first/last tile
-//     of a signal synthesises the virtual pad samples (reflect / periodic / constant / explicit
-//     halo / carried stream history) while staging, so the compute loop is boundary-agnostic
-//     (identity Q6 of SURVEY.md: padded modes == VALID over the padded signal).
-//   * shared layout: one 16-byte pad chunk after every 8 chunks -> a thread's 32-sample stride
+// Execution plan:
+//   * warp-autonomous pipeline: the unit of work is a segment of 1024 outputs of one signal (32 lanes
+//     x 32 consecutive outputs) plus halo; every warp owns two private shared-memory buffers, issues
+//     the cp.async copies (16 B, L2-only) of its next segment, waits for the current one, computes
+//     and stores.  No __syncthreads anywhere.
+//   * the first/last segment of a signal synthesises the virtual pad samples (reflect / periodic /
+//     constant / explicit halo / carried stream history) while staging -- one pad element per lane
+//     -- so the compute loop is boundary-agnostic (identity Q6 of SURVEY.md: padded modes == VALID
+//     over the padded signal).
+//   * shared layout: one 16-byte pad chunk after every 8 chunks -> a lane's 32-sample stride
 //     becomes 9 chunks (odd), every LDS.128 of the sliding window is bank-conflict free and all
 //     offsets stay compile-time immediates.
-//   * each thread produces 32 consecutive outputs from a register sliding window.  Arithmetic is
-//     packed fp32 (FFMA2, fma.rn.f32x2): accumulator pairs (out[j],out[j+1]) need the sample pair
-//     (x[j+k],x[j+k+1]), which is an aligned register pair only when j+k is even; so taps are split
-//     by parity into two accumulator sets, one holding pairs that start at even outputs and one
-//     holding pairs that start at odd outputs, merged with one add per output at the end.  Weights
-//     are uniform-register operands broadcast to both halves.
-//   * polynomial edges: warp 0 / warp 1 evaluate the n leading / trailing outputs from the
-//     transposed edge table (one lane per output) and the owners patch them in before the store.
+//   * arithmetic: register sliding window, packed fp32 (FFMA2, fma.rn.f32x2) over output pairs with
+//     the sample broadcast and the weight pair (w[k], w[k-1]) in uniform registers.
+//   * polynomial edges: one lane per edge output from the transposed edge table, patched into the
+//     owners' registers before the store.
+//   * stores go through the warp's own buffer so that each store instruction writes one contiguous
+//     run of global memory.
 #pragma once
 #include <type_traits>
 #include <utility>

@@ -12,12 +12,12 @@
 //     last strip go through a per-element edge path, so the compute is boundary agnostic.
 //   * ROW PASS: each lane owns RX consecutive columns; from a register window of the staged row it
 //     forms the folded sums s_k = x[c+k] +/- x[c-k] once and evaluates the R row factors on them
-//     (n adds + R*(n+1) FMAs per pixel instead of R*(2n+1) MACs).
+//     (n adds + R*(n+1) FMAs per pixel instead of R*(2n+1) MACs; the FMAs packed over column pairs).
 //   * COLUMN PASS, in registers: the lane keeps the 2n+1 partially accumulated output rows of its
-//     columns.  The R values just produced are scattered into them with packed FFMA2 (value broadcast,
-//     weight pair (col[k], col[k-1]) from uniform registers, output rows paired), the oldest row
-//     is complete and is stored (one 512-byte store per warp and row).  Accumulator indices are
-//     static inside blocks of U = 4 rows; a block ends with a register shift.
+//     columns.  The R values just produced are scattered into them with packed FFMA2 (column pairs
+//     packed, weight col[wy] broadcast from a uniform register), the oldest row is complete and is
+//     stored (one 512-byte store per warp and row).  Accumulator indices are static inside blocks
+//     of U = 4 rows; a block ends with a register shift.
 //   => every input pixel is read from HBM once and from shared memory (RX+2n)/RX times, no
 //      intermediate image ever exists, and there is no vertical halo recomputation except the 2n
 //      warm-up rows per band.
