@@ -227,6 +227,8 @@ def run_1d_family(wl, args, sg, lib, torch, np, dev, rank, world, barrier, max_o
 
 def run_2d(wl, args, sg, lib, torch, np, dev, rank, world, barrier, max_over_ranks, sampler, dist):
     images, rows, cols = wl["images"], wl["rows"], wl["cols"]
+    images = int(os.environ.get("SG_C4_IMAGES", images))   # experiment knobs (default = the config)
+    rows = cols = int(os.environ.get("SG_C4_SIZE", rows))
     lib.savgol_b200_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream))
     f = sg.Savgol2DFilter(wl["nx"], wl["ny"], wl["order"])
     g = torch.Generator(device=dev)

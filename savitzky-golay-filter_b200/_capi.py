@@ -115,11 +115,12 @@ def load() -> C.CDLL:
     """Loads the CUDA library; raises if it has not been built (no fallback)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("SAVGOL_B200_LIB", LIB_PATH)  # override: A/B builds of the same library
+        if not os.path.exists(path):
             raise ImportError(
-                f"{LIB_PATH} not found: build it with `make -C {os.path.join(HERE, 'csrc')} -j8` "
+                f"{path} not found: build it with `make -C {os.path.join(HERE, 'csrc')} -j8` "
                 "(or __graft_entry__.build()); this package has no CPU fallback")
-        lib = C.CDLL(LIB_PATH)
+        lib = C.CDLL(path)
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(lib, name)  # AttributeError = header/library mismatch, fail loudly
             fn.restype = res

@@ -24,6 +24,7 @@ struct Args2D {
     long long n_images;
     int boundary;
     float scale;
+    int band_rows;          // separable kernel: output rows per work item (set by the launcher)
 };
 
 cudaError_t launch_direct(const Args2D& a, bool exact, cudaStream_t stream);

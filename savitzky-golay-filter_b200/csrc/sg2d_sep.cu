@@ -28,6 +28,13 @@
 
 namespace sg { extern std::atomic<unsigned long long> g_launches; }
 
+#ifndef SG2D_KU
+#define SG2D_KU 4
+#endif
+#ifndef SG2D_MINB
+#define SG2D_MINB 4
+#endif
+
 namespace sg2d {
 
 namespace {
@@ -37,10 +44,10 @@ using sg::cp_async4;
 using sg::cp_async_commit;
 using sg::cp_async_wait;
 
-constexpr int kU = 4;         // rows per statically indexed block
+constexpr int kU = SG2D_KU;         // rows per statically indexed block
 constexpr int kRing = 8;      // staged rows per warp
 constexpr int kAhead = 6;     // prefetch distance in rows (kRing >= kAhead + 2)
-constexpr int kBand = 512;    // output rows per work item
+constexpr int kBandMax = 512; // output rows per work item (upper bound; the launcher shrinks it for small batches)
 constexpr int kWarps = 4;
 
 template <int R>
@@ -63,7 +70,7 @@ __device__ __forceinline__ int map_index(int i, int n, int boundary)
 }
 
 template <int N, int R, int RX>
-__global__ void __launch_bounds__(kWarps * 32, RX == 4 ? 4 : 3) sep_kernel(const __grid_constant__ SepW<R> w,
+__global__ void __launch_bounds__(kWarps * 32, RX == 4 ? SG2D_MINB : 3) sep_kernel(const __grid_constant__ SepW<R> w,
                                                                             const __grid_constant__ Args2D a)
 {
     constexpr int TW = 32 * RX;                 // output columns per strip
@@ -84,6 +91,7 @@ __global__ void __launch_bounds__(kWarps * 32, RX == 4 ? 4 : 3) sep_kernel(const
     const int Ylo = a.cy, Yhi = a.cy + a.out_rows;      // stored region in full-image coordinates
     const int Xlo = a.cx, Xhi = a.cx + a.out_cols;
     const int strips = (Xhi + TW - 1) / TW;
+    const int kBand = a.band_rows;
     const int bands = (a.out_rows + kBand - 1) / kBand;
     const long long per_img = static_cast<long long>(strips) * bands;
     const long long items = per_img * a.n_images;
@@ -241,13 +249,24 @@ cudaError_t launch_nr(const Args2D& a, const SepPlan& plan, cudaStream_t stream)
         bps = nb > 0 ? nb : 1;
     }
     constexpr int TW = 32 * RX;
-    const long long strips = (a.cx + a.out_cols + TW - 1) / TW, bands = (a.out_rows + kBand - 1) / kBand;
+    const long long strips = (a.cx + a.out_cols + TW - 1) / TW;
+    // band height: as tall as possible (2n warm-up rows per band are recomputed), but short enough that
+    // the launch has >= 4 work items per resident warp
+    Args2D aa = a;
+    const long long want = 4LL * sms * bps * kWarps;
+    long long nb = (want + strips * a.n_images - 1) / (strips * a.n_images);   // bands per image wanted
+    long long band = (a.out_rows + nb - 1) / (nb > 0 ? nb : 1);
+    band = (band + kU - 1) / kU * kU;
+    if (band < 8 * N + 8) band = 8 * N + 8;   // keep the warm-up overhead <= 25 %
+    if (band > kBandMax) band = kBandMax;
+    aa.band_rows = static_cast<int>(band);
+    const long long bands = (a.out_rows + band - 1) / band;
     const long long items = strips * bands * a.n_images;
     if (items <= 0) return cudaSuccess;
     long long grid = static_cast<long long>(sms) * bps;
     const long long need = (items + kWarps - 1) / kWarps;
     if (grid > need) grid = need;
-    kern<<<static_cast<unsigned>(grid), kWarps * 32, 0, stream>>>(w, a);
+    kern<<<static_cast<unsigned>(grid), kWarps * 32, 0, stream>>>(w, aa);
     sg::g_launches.fetch_add(1);
     return cudaGetLastError();
 }

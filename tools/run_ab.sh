@@ -1,0 +1,4 @@
+cd /root/repo
+for v in variants_*.so; do
+  SAVGOL_B200_LIB=/root/repo/$v python bench.py --workload c4 --steps 10 --warmup 3 --no-e2e --no-cpu 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$v', d['value'], d['ms_per_step'], d['roofline']['frac'], d['parity']['ok'])"
+done
