@@ -31,8 +31,14 @@ namespace sg { extern std::atomic<unsigned long long> g_launches; }
 #ifndef SG2D_KU
 #define SG2D_KU 4
 #endif
+#ifndef SG2D_RX4
+#define SG2D_RX4 1
+#endif
+#ifndef SG2D_MINB2
+#define SG2D_MINB2 3
+#endif
 #ifndef SG2D_MINB
-#define SG2D_MINB 4
+#define SG2D_MINB 3
 #endif
 
 namespace sg2d {
@@ -70,7 +76,7 @@ __device__ __forceinline__ int map_index(int i, int n, int boundary)
 }
 
 template <int N, int R, int RX>
-__global__ void __launch_bounds__(kWarps * 32, RX == 4 ? SG2D_MINB : 3) sep_kernel(const __grid_constant__ SepW<R> w,
+__global__ void __launch_bounds__(kWarps * 32, RX == 4 ? SG2D_MINB : SG2D_MINB2) sep_kernel(const __grid_constant__ SepW<R> w,
                                                                             const __grid_constant__ Args2D a)
 {
     constexpr int TW = 32 * RX;                 // output columns per strip
@@ -110,13 +116,22 @@ __global__ void __launch_bounds__(kWarps * 32, RX == 4 ? SG2D_MINB : 3) sep_kern
         // virtual output base: element (Y, X) of the full-size result lives at vout + Y*os + X
         float* vout = a.out + img * a.out_image_pitch - static_cast<long long>(a.cy) * a.out_stride - a.cx;
 
-        // ---- staging of input row `t` of this band (centre row Y0 - N + t) ----
-        auto stage_row = [&](int t) {
+        // ---- staging of input rows ----
+        // Interior items (no boundary rule needed in x or y -- all but the first/last band and strip)
+        // stage a row with one pointer increment and one or two unconditional 16-byte copies per lane;
+        // edge items go through the generic mapped path.
+        const bool y_in = (Y0 - N >= 0) && (Y0 - N + steps <= a.rows);
+        const bool x_in = (x0 - PADX >= 0) && (x0 + TW + PADX <= a.cols);
+        const bool fast_item = y_in && x_in;
+        float* const ring_lane = &ring[0][0] + 4 * lane;
+        // this lane's first chunk of the NEXT row to stage (valid for fast items)
+        const float* src_next = in + static_cast<long long>(Y0 - N) * a.in_stride + (x0 - PADX) + 4 * lane;
+        auto stage_generic = [&](int t) {
             const int iy = map_index(Y0 - N + t, a.rows, a.boundary);
             const float* src = in + static_cast<long long>(iy) * a.in_stride;
             float* dst = ring[t & (kRing - 1)];
             const int xb = x0 - PADX;
-#pragma unroll
+#pragma unroll 1
             for (int c = lane; c < ROWCH; c += 32) {
                 const int xin = xb + 4 * c;
                 if (xin >= 0 && xin + 3 < a.cols) {
@@ -127,11 +142,32 @@ __global__ void __launch_bounds__(kWarps * 32, RX == 4 ? SG2D_MINB : 3) sep_kern
                 }
             }
         };
+        auto stage_row = [&](int t) {
+            if (fast_item) {
+                float* dst = ring_lane + (t & (kRing - 1)) * ROWF;
+                if (ROWCH >= 32 || lane < ROWCH) cp_async16(dst, src_next);
+                if (lane < ROWCH - 32) cp_async16(dst + 128, src_next + 128);
+                src_next += a.in_stride;
+            } else {
+                stage_generic(t);
+            }
+        };
+        // store side, hoisted: this lane's columns, whether they lie inside the stored region and
+        // whether a vector store is legal; the row pointer advances by the output pitch per emitted row
+        const int X = x0 + RX * lane;
+        float* dst_row = vout + static_cast<long long>(Y0) * a.out_stride + X;
+        const bool st_vec = X >= Xlo && X + RX <= Xhi && (a.out_stride % RX) == 0 &&
+                            (reinterpret_cast<uintptr_t>(dst_row) & (4 * RX - 1)) == 0;
 
+        // Rows are consumed two per step: one wait / sync / loop overhead per two rows, and every
+        // column weight (a uniform register that has to be re-loaded each step, 46 weights do not fit
+        // the uniform register file next to everything else) is used for both rows.  An odd row count
+        // is padded with one extra (boundary-mapped) row whose contributions are never emitted.
+        const int steps2 = (steps + 1) & ~1;
         __syncwarp();  // the previous item's last reads of the ring are done
 #pragma unroll 1
-        for (int t = 0; t < kAhead; ++t) {
-            if (t < steps) stage_row(t);
+        for (int t = 0; t < kAhead; t += 2) {
+            if (t < steps2) { stage_row(t); stage_row(t + 1); }
             cp_async_commit();
         }
 
@@ -142,77 +178,95 @@ __global__ void __launch_bounds__(kWarps * 32, RX == 4 ? SG2D_MINB : 3) sep_kern
 #pragma unroll
             for (int i = 0; i < NA; ++i) acc[jp][i] = make_float2(0.f, 0.f);
 
+        // ROW PASS of the staged row t -> hp[r][jp] = (H_r at column 2jp, H_r at column 2jp+1).  The folded
+        // sums s_k = x[c+k] +/- x[c-k] are shared by the R row factors; the weighted sums run packed
+        // over column pairs (weight broadcast).
+        auto row_pass = [&](int t, float2 (&hp)[R][RX / 2]) {
+            float xs[NV * VW];
+            const float* rowp = ring_lane + (t & (kRing - 1)) * ROWF + (RX - 4) * lane;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                if constexpr (VW == 4) {
+                    const float4 q = *reinterpret_cast<const float4*>(rowp + 4 * v);
+                    xs[4 * v] = q.x; xs[4 * v + 1] = q.y; xs[4 * v + 2] = q.z; xs[4 * v + 3] = q.w;
+                } else {
+                    const float2 q = *reinterpret_cast<const float2*>(rowp + 2 * v);
+                    xs[2 * v] = q.x; xs[2 * v + 1] = q.y;
+                }
+            }
+#pragma unroll
+            for (int jp = 0; jp < RX / 2; ++jp) {
+                const int c0 = 2 * jp + DX + N;
+                const float2 ctr = make_float2(xs[c0], xs[c0 + 1]);
+#pragma unroll
+                for (int r = 0; r < R; ++r) hp[r][jp] = __fmul2_rn(make_float2(w.rc[r], w.rc[r]), ctr);
+            }
+#pragma unroll
+            for (int k = 1; k <= N; ++k)
+#pragma unroll
+                for (int jp = 0; jp < RX / 2; ++jp) {
+                    const int c0 = 2 * jp + DX + N;
+                    const float2 sk = make_float2(fmaf(w.sx, xs[c0 - k], xs[c0 + k]),      // +/-1 multiply is exact
+                                                  fmaf(w.sx, xs[c0 + 1 - k], xs[c0 + 1 + k]));
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        hp[r][jp] = __ffma2_rn(make_float2(w.rk[r][k - 1], w.rk[r][k - 1]), sk, hp[r][jp]);
+                }
+        };
+        auto emit = [&](const float2 (&v)[RX / 2]) {
+            if (st_vec) {
+                if constexpr (RX == 4) sg::st_cs_f4(dst_row, make_float4(v[0].x, v[0].y, v[1].x, v[1].y));
+                else *reinterpret_cast<float2*>(dst_row) = v[0];
+            } else {
+#pragma unroll
+                for (int j = 0; j < RX; ++j)
+                    if (X + j >= Xlo && X + j < Xhi) dst_row[j] = (j & 1) ? v[j / 2].y : v[j / 2].x;
+            }
+            dst_row += a.out_stride;
+        };
+
 #pragma unroll 1
-        for (int tb = 0; tb * kU < steps; ++tb) {
+        for (int tb = 0; tb * kU < steps2; ++tb) {
 #pragma unroll
-            for (int u = 0; u < kU; ++u) {
+            for (int u = 0; u < kU; u += 2) {
                 const int t = tb * kU + u;
-                if (t < steps) {
-                    if (t + kAhead < steps) stage_row(t + kAhead);
+                if (t < steps2) {
+                    cp_async_wait<kAhead / 2 - 1>();   // rows t and t+1 have landed (this lane's part) ...
+                    __syncwarp();                      // ... and everybody else's; rows t-2, t-1 are fully consumed
+                    if (t + kAhead < steps2) { stage_row(t + kAhead); stage_row(t + kAhead + 1); }   // into their slots
                     cp_async_commit();
-                    cp_async_wait<kAhead>();   // row t has landed (this lane's part) ...
-                    __syncwarp();              // ... and everybody else's
 
-                    // ---- row pass ----
-                    float xs[NV * VW];
-                    const float* rowp = ring[t & (kRing - 1)] + RX * lane;
-#pragma unroll
-                    for (int v = 0; v < NV; ++v) {
-                        if constexpr (VW == 4) {
-                            const float4 q = *reinterpret_cast<const float4*>(rowp + 4 * v);
-                            xs[4 * v] = q.x; xs[4 * v + 1] = q.y; xs[4 * v + 2] = q.z; xs[4 * v + 3] = q.w;
-                        } else {
-                            const float2 q = *reinterpret_cast<const float2*>(rowp + 2 * v);
-                            xs[2 * v] = q.x; xs[2 * v + 1] = q.y;
-                        }
-                    }
-                    // folded sums s_k = x[c+k] +/- x[c-k] are shared by the R row factors; the weighted
-                    // sums run packed over column pairs (weight broadcast)
-                    float2 hp[R][RX / 2];
-#pragma unroll
-                    for (int jp = 0; jp < RX / 2; ++jp) {
-                        const int c0 = 2 * jp + DX + N;
-                        const float2 ctr = make_float2(xs[c0], xs[c0 + 1]);
-#pragma unroll
-                        for (int r = 0; r < R; ++r) hp[r][jp] = __fmul2_rn(make_float2(w.rc[r], w.rc[r]), ctr);
-#pragma unroll
-                        for (int k = 1; k <= N; ++k) {
-                            const float2 sk = make_float2(fmaf(w.sx, xs[c0 - k], xs[c0 + k]),      // +/-1 multiply is exact
-                                                          fmaf(w.sx, xs[c0 + 1 - k], xs[c0 + 1 + k]));
-#pragma unroll
-                            for (int r = 0; r < R; ++r)
-                                hp[r][jp] = __ffma2_rn(make_float2(w.rk[r][k - 1], w.rk[r][k - 1]), sk, hp[r][jp]);
-                        }
-                    }
+                    float2 h0[R][RX / 2], h1[R][RX / 2];
+                    row_pass(t, h0);
+                    row_pass(t + 1, h1);
 
-                    // ---- column pass: scatter the new row into the 2n+1 output rows in flight ----
-                    // output row i of the block window sees this input row as window row wy = u + 2n - i
+                    // ---- column pass: scatter both rows into the output rows in flight ----
+                    // row t is window row wy of output i = u + 2n - wy; row t+1 is window row wy of output i+1
 #pragma unroll
-                    for (int jp = 0; jp < RX / 2; ++jp)
+                    for (int wy = 0; wy <= 2 * N; ++wy)
 #pragma unroll
-                        for (int r = 0; r < R; ++r)
+                        for (int r = 0; r < R; ++r) {
+                            const float cw = w.col[r][wy];
+                            const int i = u + 2 * N - wy;
 #pragma unroll
-                            for (int i = u; i <= u + 2 * N; ++i) {
-                                const float cw = w.col[r][u + 2 * N - i];
-                                acc[jp][i] = __ffma2_rn(make_float2(cw, cw), hp[r][jp], acc[jp][i]);
+                            for (int jp = 0; jp < RX / 2; ++jp) {
+                                acc[jp][i] = __ffma2_rn(make_float2(cw, cw), h0[r][jp], acc[jp][i]);
+                                acc[jp][i + 1] = __ffma2_rn(make_float2(cw, cw), h1[r][jp], acc[jp][i + 1]);
                             }
-
-                    // ---- the oldest output row (index u of the block) is complete ----
-                    if (t >= 2 * N) {
-                        const int Y = Y0 + t - 2 * N;
-                        const int X = x0 + RX * lane;
-                        float o[RX];
-#pragma unroll
-                        for (int jp = 0; jp < RX / 2; ++jp) { o[2 * jp] = acc[jp][u].x; o[2 * jp + 1] = acc[jp][u].y; }
-                        float* dst = vout + static_cast<long long>(Y) * a.out_stride + X;
-                        if (X >= Xlo && X + RX <= Xhi && (reinterpret_cast<uintptr_t>(dst) & (4 * RX - 1)) == 0) {
-                            if constexpr (RX == 4) sg::st_cs_f4(dst, make_float4(o[0], o[1], o[2], o[3]));
-                            else *reinterpret_cast<float2*>(dst) = make_float2(o[0], o[1]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < RX; ++j)
-                                if (X + j >= Xlo && X + j < Xhi) dst[j] = o[j];
                         }
+
+                    // ---- output rows u and u+1 of the block are complete ----
+                    if (t >= 2 * N && t - 2 * N < nrows) {
+                        float2 v[RX / 2];
+#pragma unroll
+                        for (int jp = 0; jp < RX / 2; ++jp) v[jp] = acc[jp][u];
+                        emit(v);
+                    }
+                    if (t + 1 >= 2 * N && t + 1 - 2 * N < nrows) {
+                        float2 v[RX / 2];
+#pragma unroll
+                        for (int jp = 0; jp < RX / 2; ++jp) v[jp] = acc[jp][u + 1];
+                        emit(v);
                     }
                 }
             }
@@ -229,7 +283,7 @@ __global__ void __launch_bounds__(kWarps * 32, RX == 4 ? SG2D_MINB : 3) sep_kern
 template <int N, int R>
 cudaError_t launch_nr(const Args2D& a, const SepPlan& plan, cudaStream_t stream)
 {
-    constexpr int RX = N <= 8 ? 4 : 2;
+    constexpr int RX = (N <= 8 && SG2D_RX4) ? 4 : 2;
     SepW<R> w;
     const float sc = a.scale;
     for (int r = 0; r < R; ++r) {
