@@ -145,3 +145,21 @@ def test_apply_fails_loudly_without_gpu(capfd):
         f.apply(x)
     assert "no CPU fallback" in capfd.readouterr().err
     assert f.apply_valid(x).size == 0
+
+
+def test_reference_export_tool_on_our_library_emits_identical_header(tmp_path):
+    """The reference's coefficient export CLI (src/savgol_export.c, reads f->center_weights /
+    f->edge_weights / f->window_size directly) compiled unmodified against libsavgol_b200 must print
+    the same header as when built against the reference library -- struct layout + weight parity."""
+    import subprocess
+    ours = os.path.join(ROOT, "oracle", "_ref", "savgol_export_b200")
+    ref = os.path.join(ROOT, "oracle", "_ref", "savgol_export_ref")
+    if not (os.path.exists(ours) and os.path.exists(ref)):
+        pytest.skip("drop-in binaries not built (make -C oracle dropin)")
+    for n, m, d in [(12, 4, 0), (16, 3, 1), (32, 4, 2), (5, 2, 2)]:
+        a, b = tmp_path / "a.h", tmp_path / "b.h"
+        for exe, out in ((ours, a), (ref, b)):
+            subprocess.run([exe, "-n", str(n), "-m", str(m), "-d", str(d), "-o", str(out)], check=True,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        strip = lambda p: [l for l in open(p).read().splitlines() if "enerated" not in l]
+        assert strip(a) == strip(b), (n, m, d)
