@@ -29,7 +29,19 @@ int mode_of(const SavgolFilter* f)
     }
 }
 
-constexpr size_t kChunkFloats = size_t(16) << 20;  // 64 MiB of samples per staged chunk
+static size_t chunk_floats()
+{
+    // samples per staged chunk: small enough that pipeline fill + drain (one chunk each way) is a few
+    // percent of a large transfer, large enough to stay near PCIe peak.  Env override for experiments.
+    static size_t v = [] {
+        const char* e = getenv("SAVGOL_B200_CHUNK_MIB");
+        size_t mib = e ? static_cast<size_t>(atoi(e)) : 64;  // measured on B200: 64 MiB 23.0 ms/GiB-step, 16 MiB 23.2, 4 MiB 26.9
+        if (mib < 1) mib = 1;
+        return mib << 18;
+    }();
+    return v;
+}
+#define kChunkFloats chunk_floats()
 
 // Batch of contiguous-sample rows living in HOST memory (in and out both host).
 // Rows short enough are grouped into chunks of whole rows; a row longer than a chunk is cut
