@@ -31,6 +31,9 @@ namespace sg { extern std::atomic<unsigned long long> g_launches; }
 #ifndef SG2D_KU
 #define SG2D_KU 4
 #endif
+#ifndef SG2D_RXW
+#define SG2D_RXW 4
+#endif
 #ifndef SG2D_RX4
 #define SG2D_RX4 1
 #endif
@@ -76,7 +79,7 @@ __device__ __forceinline__ int map_index(int i, int n, int boundary)
 }
 
 template <int N, int R, int RX>
-__global__ void __launch_bounds__(kWarps * 32, RX == 4 ? SG2D_MINB : SG2D_MINB2) sep_kernel(const __grid_constant__ SepW<R> w,
+__global__ void __launch_bounds__(kWarps * 32, RX >= 4 ? SG2D_MINB : SG2D_MINB2) sep_kernel(const __grid_constant__ SepW<R> w,
                                                                             const __grid_constant__ Args2D a)
 {
     constexpr int TW = 32 * RX;                 // output columns per strip
@@ -86,7 +89,7 @@ __global__ void __launch_bounds__(kWarps * 32, RX == 4 ? SG2D_MINB : SG2D_MINB2)
     constexpr int ROWCH = ROWF / 4;             // 16-byte chunks per staged row
     constexpr int NA = 2 * N + kU;              // output rows in flight per column (block-static window)
     constexpr int WIN = RX + DX + 2 * N;        // floats of the row window a lane touches
-    constexpr int VW = RX == 4 ? 4 : 2;         // floats per shared load
+    constexpr int VW = RX >= 4 ? 4 : 2;         // floats per shared load
     constexpr int NV = (WIN + VW - 1) / VW;
 
     __shared__ __align__(16) float s_ring[kWarps][kRing][ROWF];
@@ -145,8 +148,9 @@ __global__ void __launch_bounds__(kWarps * 32, RX == 4 ? SG2D_MINB : SG2D_MINB2)
         auto stage_row = [&](int t) {
             if (fast_item) {
                 float* dst = ring_lane + (t & (kRing - 1)) * ROWF;
-                if (ROWCH >= 32 || lane < ROWCH) cp_async16(dst, src_next);
-                if (lane < ROWCH - 32) cp_async16(dst + 128, src_next + 128);
+#pragma unroll
+                for (int c0 = 0; c0 < ROWCH; c0 += 32)
+                    if (c0 + 32 <= ROWCH || lane < ROWCH - c0) cp_async16(dst + 4 * c0, src_next + 4 * c0);
                 src_next += a.in_stride;
             } else {
                 stage_generic(t);
@@ -156,8 +160,9 @@ __global__ void __launch_bounds__(kWarps * 32, RX == 4 ? SG2D_MINB : SG2D_MINB2)
         // whether a vector store is legal; the row pointer advances by the output pitch per emitted row
         const int X = x0 + RX * lane;
         float* dst_row = vout + static_cast<long long>(Y0) * a.out_stride + X;
-        const bool st_vec = X >= Xlo && X + RX <= Xhi && (a.out_stride % RX) == 0 &&
-                            (reinterpret_cast<uintptr_t>(dst_row) & (4 * RX - 1)) == 0;
+        constexpr int SV = RX >= 4 ? 4 : 2;  // floats per store instruction
+        const bool st_vec = X >= Xlo && X + RX <= Xhi && (a.out_stride % SV) == 0 &&
+                            (reinterpret_cast<uintptr_t>(dst_row) & (4 * SV - 1)) == 0;
 
         // Rows are consumed two per step: one wait / sync / loop overhead per two rows, and every
         // column weight (a uniform register that has to be re-loaded each step, 46 weights do not fit
@@ -215,8 +220,13 @@ __global__ void __launch_bounds__(kWarps * 32, RX == 4 ? SG2D_MINB : SG2D_MINB2)
         };
         auto emit = [&](const float2 (&v)[RX / 2]) {
             if (st_vec) {
-                if constexpr (RX == 4) sg::st_cs_f4(dst_row, make_float4(v[0].x, v[0].y, v[1].x, v[1].y));
-                else *reinterpret_cast<float2*>(dst_row) = v[0];
+                if constexpr (RX >= 4) {
+#pragma unroll
+                    for (int q = 0; q < RX / 4; ++q)
+                        sg::st_cs_f4(dst_row + 4 * q, make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y));
+                } else {
+                    *reinterpret_cast<float2*>(dst_row) = v[0];
+                }
             } else {
 #pragma unroll
                 for (int j = 0; j < RX; ++j)
@@ -283,7 +293,7 @@ __global__ void __launch_bounds__(kWarps * 32, RX == 4 ? SG2D_MINB : SG2D_MINB2)
 template <int N, int R>
 cudaError_t launch_nr(const Args2D& a, const SepPlan& plan, cudaStream_t stream)
 {
-    constexpr int RX = (N <= 8 && SG2D_RX4) ? 4 : 2;
+    constexpr int RX = (N <= 8 && SG2D_RX4) ? SG2D_RXW : 2;
     SepW<R> w;
     const float sc = a.scale;
     for (int r = 0; r < R; ++r) {
