@@ -211,3 +211,32 @@ def test_host_pointer_path_chunks(oracle):
     yp = torch.empty_like(xp).pin_memory()
     f.apply(xp, out=yp)
     assert np.array_equal(bits(yp.numpy()), bits(y))
+
+
+def test_signal_longer_than_2_31_samples_periodic(oracle):
+    """BASELINE config 3 scale: the reference's padded modes overflow `int` here (SIGFPE at 2^32,
+    SURVEY.md Q5).  Checked through the Q6 identity (periodic == VALID over the wrap-padded signal)
+    on both ends, around the 2^31 index and on random interior windows."""
+    free, _ = torch.cuda.mem_get_info()
+    L = (1 << 31) + 12345
+    if free < 2 * 4 * L + (2 << 30):
+        pytest.skip("not enough device memory")
+    n, m, d = 32, 4, 2
+    g = torch.Generator(device="cuda"); g.manual_seed(2)
+    x = torch.empty(L, device="cuda", dtype=torch.float32)
+    step = 1 << 28
+    for a in range(0, L, step):
+        x[a:a + step].normal_(generator=g)
+    f = sg.SavgolFilter(n, m, d, 1.0, "periodic")
+    y = f.apply(x)
+    o = oracle.Filter1D(n, m, d, 1.0, "periodic")
+    W = 5000
+    tol_ = 1e-6 * 6.0
+    head = torch.cat([x[L - n:], x[:W + n]]).cpu().numpy()
+    tail = torch.cat([x[L - W - n:], x[:n]]).cpu().numpy()
+    assert np.max(np.abs(o.apply_valid(head) - y[:W].cpu().numpy())) <= tol_
+    assert np.max(np.abs(o.apply_valid(tail) - y[L - W:].cpu().numpy())) <= tol_
+    rng = np.random.default_rng(0)
+    for c in [1 << 31, (1 << 31) - 1000, 1 << 30] + [int(v) for v in rng.integers(W, L - 2 * W, 6)]:
+        seg = x[c - n:c + W + n].cpu().numpy()
+        assert np.max(np.abs(o.apply_valid(seg) - y[c:c + W].cpu().numpy())) <= tol_, c
