@@ -333,6 +333,52 @@ int savgol2d_laplacian(int hx, int hy, int order, const float* input, int rows, 
         return -1;
     }
     if (!input || !output) return -1;
+    // Fused path (default arithmetic): d2/dx2 + d2/dy2 of the fitted polynomial is ONE weight table,
+    //   W = Wxx / dx^2 + Wyy / dy^2,
+    // again a polynomial surface of the same degree, so it goes through the separable kernel in a
+    // single pass (one image read, one write) instead of two filters plus an add
+    // (ref composition: src/savgol2d.c:560-618; the exact flavour below keeps that composition).
+    if (!sge::exact_mode()) {
+        Savgol2DConfig cxx, cyy;
+        memset(&cxx, 0, sizeof(cxx));
+        cxx.half_window_x = static_cast<uint8_t>(hx); cxx.half_window_y = static_cast<uint8_t>(hy);
+        cxx.poly_order = static_cast<uint8_t>(order); cxx.deriv_x = 2; cxx.deriv_y = 0;
+        cxx.delta_x = delta_x; cxx.delta_y = delta_y;
+        cyy = cxx; cyy.deriv_x = 0; cyy.deriv_y = 2;
+        if (!savgol2d_config_valid(&cxx) || !savgol2d_config_valid(&cyy)) {
+            fprintf(stderr, "savgol2d_create: invalid configuration\n");
+            return -1;
+        }
+        const int area = (2 * hx + 1) * (2 * hy + 1);
+        std::vector<float> wxx(area), wyy(area), wl(area);
+        double kxx[28], kyy[28], kl[28];
+        if (sgc::weights2d(hx, hy, order, 2, 0, wxx.data(), kxx) && sgc::weights2d(hx, hy, order, 0, 2, wyy.data(), kyy)) {
+            const double sxx = static_cast<double>(sgc::scale2d(2, 0, delta_x, delta_y));
+            const double syy = static_cast<double>(sgc::scale2d(0, 2, delta_x, delta_y));
+            for (int k = 0; k < area; ++k) wl[k] = static_cast<float>(wxx[k] * sxx + wyy[k] * syy);
+            for (int k = 0; k < 28; ++k) kl[k] = kxx[k] * sxx + kyy[k] * syy;
+            Filter2DImpl* fi = static_cast<Filter2DImpl*>(calloc(1, sizeof(Filter2DImpl)));
+            float* wt = static_cast<float*>(malloc(static_cast<size_t>(area) * sizeof(float)));
+            if (fi && wt) {
+                memcpy(wt, wl.data(), static_cast<size_t>(area) * sizeof(float));
+                fi->pub.config = cxx;
+                fi->pub.window_width = 2 * hx + 1; fi->pub.window_height = 2 * hy + 1; fi->pub.window_area = area;
+                fi->pub.num_terms = savgol2d_num_terms(order);
+                fi->pub.scale = 1.0f;   // both scales are folded into the table
+                fi->pub.weights = wt;
+                sg2d::plan_separable(hx, hy, order, kl, wt, &fi->plan);
+                fi->magic = kMagic2D;
+                {
+                    std::lock_guard<std::mutex> lk(g_mu2d);
+                    g_live2d.insert(fi);
+                }
+                const int rcf = savgol2d_apply(&fi->pub, input, rows, cols, stride, output, stride, boundary);
+                savgol2d_destroy(&fi->pub);
+                return rcf;
+            }
+            free(fi); free(wt);
+        }
+    }
     int rc = component(hx, hy, order, 2, 0, input, rows, cols, stride, output, delta_x, delta_y, boundary);
     if (rc != 0) return rc;
     const size_t span = static_cast<size_t>(rows) * stride;

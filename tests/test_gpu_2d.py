@@ -132,3 +132,21 @@ def test_errors_like_reference():
     assert lib.savgol2d_apply_valid(f.handle, x.data_ptr(), 5, 5, 5, x.data_ptr(), 5) == -1   # ref: src/savgol2d.c:371
     assert lib.savgol2d_apply(f.handle, None, 5, 5, 5, x.data_ptr(), 5, 1) == -1
     assert lib.savgol2d_apply(f.handle, x.data_ptr(), 5, 5, 5, x.data_ptr(), 5, 0) == -1
+
+
+def test_laplacian_is_one_fused_pass(oracle):
+    # W_lap = Wxx/dx^2 + Wyy/dy^2 is one polynomial weight table -> one separable launch
+    rng = np.random.default_rng(12)
+    img = rng.standard_normal((300, 400)).astype(np.float32)
+    d = torch.from_numpy(img).cuda()
+    c0 = sg.launch_count()
+    lap = sg.laplacian(d, 7, 7, 3, 1.0, 1.0, "constant")
+    torch.cuda.synchronize()
+    assert sg.launch_count() - c0 == 1
+    want = oracle.Filter2D(7, 7, 3, 2, 0).apply(img, "constant") + oracle.Filter2D(7, 7, 3, 0, 2).apply(img, "constant")
+    assert np.max(np.abs(lap.cpu().numpy() - want)) <= 1e-6 * float(np.abs(img).max())
+    # the exact flavour keeps the reference's composition (two filters + add) bit for bit
+    sg.set_exact(True)
+    lap_e = sg.laplacian(d, 7, 7, 3, 1.0, 1.0, "constant")
+    sg.set_exact(False)
+    assert np.array_equal(bits(lap_e.cpu().numpy()), bits(want))
