@@ -245,6 +245,11 @@ def main():
 
     wl = WORKLOADS[args.workload]
     lib = sg.lib()
+    traffic = None
+    try:  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get("bytes")
+    except Exception:
+        pass
     peaks, peak_kind = measured_peaks()
     sampler = ClockSampler(local)
     extra = {}
@@ -271,7 +276,7 @@ def main():
                             else "L2 flushed between steps by a 256 MiB memset", "sharding": "independent units per rank, no collective"
                             if wl["kind"] != "long" else "contiguous slices, n-sample halo all_gather per step"}, **res.get("config", {})),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": res.get("traffic"), "peak_kind": peak_kind,
+                         "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": res.get("traffic", traffic), "peak_kind": peak_kind,
                          "kernel": res["kernel"], "kernel_ms": round(kern_ms, 5), "alg_bytes_per_launch": alg_bytes},
             "clocks": res["clocks"],
             "gpu_launches": res["gpu_launches"],
