@@ -152,8 +152,26 @@ bool run1d_any(const SavgolFilter* f, const float* in, float* out, size_t rows, 
         p.mode = mode; p.edge_lead = p.edge_trail = poly_edges; p.arith = arith;
         return sge::run1d_device(p, sge::current_stream());
     }
-    if (ki != MemKind::Device && ko != MemKind::Device)
+    if (ki != MemKind::Device && ko != MemKind::Device) {
+        // Experiment knob: pinned host buffers can be read / written by the kernel directly over PCIe
+        // (zero copy, no staging ring).  Off by default -- see DESIGN.md section 5 for the measurement.
+        static const int zero_copy = [] { const char* e = getenv("SAVGOL_B200_ZEROCOPY"); return (e && e[0] == '1') ? 1 : 0; }();
+        if (zero_copy && ki == MemKind::Pinned && ko == MemKind::Pinned && in != out) {
+            void *din = nullptr, *dout = nullptr;
+            if (cudaHostGetDevicePointer(&din, const_cast<float*>(in), 0) == cudaSuccess &&
+                cudaHostGetDevicePointer(&dout, out, 0) == cudaSuccess) {
+                sge::Problem1D p{};
+                p.filter = f; p.in = din; p.out = dout; p.rows = rows; p.len = len;
+                p.in_row_bytes = in_pitch * sizeof(float); p.out_row_bytes = out_pitch * sizeof(float);
+                p.in_stride = p.out_stride = 4;
+                p.mode = mode; p.edge_lead = p.edge_trail = poly_edges; p.arith = arith;
+                cudaStream_t st = sge::current_stream();
+                return sge::run1d_device(p, st) && cuda_ok(cudaStreamSynchronize(st), "sync");
+            }
+            (void)cudaGetLastError();
+        }
         return run1d_host(f, in, out, rows, len, in_pitch, out_pitch, mode, poly_edges, arith);
+    }
     fprintf(stderr, "savgol_b200: input and output must both be device pointers or both be host pointers\n");
     return false;
 }
