@@ -128,6 +128,19 @@ __device__ __forceinline__ void stage_segment(float4* dst0 /* buf + lane + (lane
             const int c = lane + 32 * it;  // chunk c lives at c + (c >> 3) = dst0 + 36*it
             if (c >= c_lo && c < c_hi) cp_async16(dst0 + 36 * it, s + 512 * it);
         }
+    } else if (a.in_stride == 4) {
+        // contiguous row that is not 16-byte aligned (odd pitch, offset view): lane-consecutive 4-byte
+        // copies, i.e. every copy instruction still covers one contiguous 128-byte run.  Element
+        // e = lane + 32 i lives at float position e + 4 (e >> 5) = lane + 36 i of the padded buffer.
+        constexpr int NE = (4 * ((kSeg + 2 * N + DELTA + 3) / 4) + 31) / 32;
+        float* d = reinterpret_cast<float*>(buf) + lane;
+        const char* s = src0 + 4 * lane;
+        const int e_lo = 4 * c_lo, e_hi = 4 * c_hi;
+#pragma unroll
+        for (int i = 0; i < NE; ++i) {
+            const int e = lane + 32 * i;
+            if (e >= e_lo && e < e_hi) cp_async4(d + 36 * i, s + 128 * i);
+        }
     } else {
         const long long st = a.in_stride;
 #pragma unroll 1
@@ -394,12 +407,22 @@ __global__ void __launch_bounds__(kThreads, SG_MIN_BLOCKS) sg1d_kernel(const __g
             for (int i = 0; i < kR / 4; ++i) st_cs_f4(dst + 128 * i, src[36 * i]);  // chunk lane + 32 i
         } else {
             const int lim = remain < kSeg ? static_cast<int>(remain) : kSeg;
-            const float* srcf = reinterpret_cast<const float*>(buf_cur);
+            // lane-interleaved scalar stores (ragged last segment, misaligned or strided rows): output
+            // f = lane + 32 i of the segment is parked at float position f + 4 (f >> 5) = lane + 36 i
+            const float* srcf = reinterpret_cast<const float*>(buf_cur) + lane;
+            if (a.out_stride == 4) {
+                float* dst = reinterpret_cast<float*>(orow) + o0 + lane;
+#pragma unroll
+                for (int i = 0; i < kR; ++i)
+                    if (lane + 32 * i < lim) dst[32 * i] = srcf[36 * i];
+            } else {
+                char* dst = orow + (o0 + lane) * a.out_stride;
+                const long long step = 32 * a.out_stride;
 #pragma unroll 4
-            for (int i = 0; i < kR; ++i) {
-                const int f = 32 * i + lane;  // output index inside the segment; lives at chunk f/4 (+pad), word f%4
-                if (f < lim)
-                    *reinterpret_cast<float*>(orow + (o0 + f) * a.out_stride) = srcf[4 * ((f >> 2) + (f >> 5)) + (f & 3)];
+                for (int i = 0; i < kR; ++i) {
+                    if (lane + 32 * i < lim) *reinterpret_cast<float*>(dst) = srcf[36 * i];
+                    dst += step;
+                }
             }
         }
         __syncwarp();  // all lanes are done with buf_cur and s_edge[warp] before the refill
