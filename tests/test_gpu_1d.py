@@ -240,3 +240,28 @@ def test_signal_longer_than_2_31_samples_periodic(oracle):
     for c in [1 << 31, (1 << 31) - 1000, 1 << 30] + [int(v) for v in rng.integers(W, L - 2 * W, 6)]:
         seg = x[c - n:c + W + n].cpu().numpy()
         assert np.max(np.abs(o.apply_valid(seg) - y[c:c + W].cpu().numpy())) <= tol_, c
+
+
+@pytest.mark.parametrize("n,m,d,dt", [(1, 1, 0, 1.0), (4, 2, 1, 0.5), (12, 4, 0, 1.0), (16, 3, 1, 1.0), (25, 4, 2, 1.0), (32, 5, 0, 1.0)])
+def test_short_row_batches_share_warps(oracle, n, m, d, dt):
+    # rows of <= 512 samples run in the packed kernel (2, 4 or 8 signals per warp, sg1d_packed.cuh):
+    # every packing width, ragged row counts, aligned / odd pitches, offset views
+    rng = np.random.default_rng(77 + n)
+    ws = 2 * n + 1
+    lengths = sorted({ws, ws + 1, 100 + n, 128, 129, 200, 256, 257, 360, 511, 512})
+    for L in lengths:
+        for rows in (2, 3, 9, 64, 333):
+            pitch = L + (0 if rows % 2 == 0 else 3)
+            big = torch.from_numpy(rng.standard_normal((rows, pitch + 1)).astype(np.float32)).cuda()
+            off = 1 if rows == 9 else 0
+            x = big[:, off:off + L]
+            xh = x.cpu().numpy().copy()
+            mode = MODES[(L + rows) % 4]
+            f = sg.SavgolFilter(n, m, d, dt, mode)
+            ref = oracle.Filter1D(n, m, d, dt, mode).apply(xh)
+            out = torch.full((rows, pitch + 1), 7.0, device="cuda")
+            f.apply(x, out=out[:, off:off + L])
+            y = out[:, off:off + L].cpu().numpy()
+            assert np.max(np.abs(y - ref)) <= tol(xh, dt, d), (n, L, rows, mode, float(np.max(np.abs(y - ref))))
+            assert torch.all(out[:, :off] == 7.0) and torch.all(out[:, off + L:] == 7.0), (n, L, rows)
+            f.close()
