@@ -25,6 +25,7 @@ struct Args2D {
     int boundary;
     float scale;
     int band_rows;          // separable kernel: output rows per work item (set by the launcher)
+    unsigned* counter;      // separable kernel: work-item ticket counter, zeroed in stream order before the launch
 };
 
 cudaError_t launch_direct(const Args2D& a, bool exact, cudaStream_t stream);

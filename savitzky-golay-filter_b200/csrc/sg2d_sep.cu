@@ -22,9 +22,11 @@
 //      intermediate image ever exists, and there is no vertical halo recomputation except the 2n
 //      warm-up rows per band.
 #include <atomic>
+#include <mutex>
 
 #include "sg2d.h"
 #include "sg_common.cuh"
+#include "sg1d_kernel.cuh"  // static_for
 
 namespace sg { extern std::atomic<unsigned long long> g_launches; }
 
@@ -37,11 +39,14 @@ namespace sg { extern std::atomic<unsigned long long> g_launches; }
 #ifndef SG2D_RX4
 #define SG2D_RX4 1
 #endif
+#ifndef SG2D_RING
+#define SG2D_RING 1
+#endif
 #ifndef SG2D_MINB2
 #define SG2D_MINB2 3
 #endif
 #ifndef SG2D_MINB
-#define SG2D_MINB 3
+#define SG2D_MINB 4
 #endif
 
 namespace sg2d {
@@ -78,6 +83,55 @@ __device__ __forceinline__ int map_index(int i, int n, int boundary)
     return i;
 }
 
+// Run f(integral_constant<I>) for the I that equals `v` (0 <= v < COUNT).
+template <class F, int... I>
+__device__ __forceinline__ void static_switch_impl(int v, F&& f, std::integer_sequence<int, I...>)
+{
+    (void)((v == I && (f(std::integral_constant<int, I>{}), true)) || ...);
+}
+template <int COUNT, class F>
+__device__ __forceinline__ void static_switch(int v, F&& f)
+{
+    static_switch_impl(v, static_cast<F&&>(f), std::make_integer_sequence<int, COUNT>{});
+}
+
+// Stores of a lane whose columns straddle the stored region or whose row is not vector-aligned.
+template <int RX>
+__device__ __noinline__ void emit_ragged(float* dst_row, const float2 (&v)[RX / 2], int X, int Xlo, int Xhi)
+{
+#pragma unroll
+    for (int j = 0; j < RX; ++j)
+        if (X + j >= Xlo && X + j < Xhi) dst_row[j] = (j & 1) ? v[j / 2].y : v[j / 2].x;
+}
+
+__device__ __forceinline__ void cp_async16_s(unsigned smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+
+// Rows y, y+1 of an edge item (first / last band or strip) into two consecutive ring slots: the row
+// index goes through the boundary rule, chunks that exist are copied 16 bytes at a time, pad columns
+// element by element from the column the rule maps them to.  Out of line: 1/16 of the items of a 4096^2
+// image take it, it must not bloat the main loop.
+__device__ __noinline__ void stage_mapped(float* dst, const float* in, int y, int xb, int rows, int cols, long long stride,
+                                          int boundary, int rowf, int lane)
+{
+#pragma unroll 1
+    for (int rr = 0; rr < 2; ++rr, dst += rowf) {
+        const float* src = in + static_cast<long long>(map_index(y + rr, rows, boundary)) * stride;
+#pragma unroll 1
+        for (int c = lane; 4 * c < rowf; c += 32) {
+            const int xin = xb + 4 * c;
+            if (xin >= 0 && xin + 3 < cols) {
+                cp_async16(dst + 4 * c, src + xin);
+            } else {
+#pragma unroll 1
+                for (int e = 0; e < 4; ++e) cp_async4(dst + 4 * c + e, src + map_index(xin + e, cols, boundary));
+            }
+        }
+    }
+}
+
 template <int N, int R, int RX>
 __global__ void __launch_bounds__(kWarps * 32, RX >= 4 ? SG2D_MINB : SG2D_MINB2) sep_kernel(const __grid_constant__ SepW<R> w,
                                                                             const __grid_constant__ Args2D a)
@@ -87,7 +141,8 @@ __global__ void __launch_bounds__(kWarps * 32, RX >= 4 ? SG2D_MINB : SG2D_MINB2)
     constexpr int DX = PADX - N;
     constexpr int ROWF = TW + 2 * PADX;         // floats per staged row
     constexpr int ROWCH = ROWF / 4;             // 16-byte chunks per staged row
-    constexpr int NA = 2 * N + kU;              // output rows in flight per column (block-static window)
+    constexpr bool RING = SG2D_RING && N <= 8;  // static accumulator ring (main loop unrolled n+1 steps) vs shifting blocks
+    constexpr int NA = RING ? 2 * N + 2 : 2 * N + kU;   // output rows in flight per column
     constexpr int WIN = RX + DX + 2 * N;        // floats of the row window a lane touches
     constexpr int VW = RX >= 4 ? 4 : 2;         // floats per shared load
     constexpr int NV = (WIN + VW - 1) / VW;
@@ -104,12 +159,34 @@ __global__ void __launch_bounds__(kWarps * 32, RX >= 4 ? SG2D_MINB : SG2D_MINB2)
     const int bands = (a.out_rows + kBand - 1) / kBand;
     const long long per_img = static_cast<long long>(strips) * bands;
     const long long items = per_img * a.n_images;
-    const long long nwarps = static_cast<long long>(gridDim.x) * kWarps;
 
-    for (long long item = static_cast<long long>(blockIdx.x) * kWarps + warp; item < items; item += nwarps) {
-        const long long img = item / per_img;
-        const int rem = static_cast<int>(item - img * per_img);
-        const int band = rem / strips, strip = rem - band * strips;
+    // Work items are handed out dynamically (one atomic per item): edge strips / bands take longer than
+    // interior ones, a static round-robin leaves warps idle at the end of the launch.
+    for (;;) {
+        unsigned ticket = 0;
+        if (lane == 0) ticket = atomicAdd(a.counter, 1u);
+        const long long item = __shfl_sync(0xffffffffu, ticket, 0);
+        if (item >= items) break;
+        // longest first: the items of the two edge strips (out-of-line staging, several times slower)
+        // are handed out before everything else, so none of them is left for the tail of the launch;
+        // the interior strips follow image by image, band by band, neighbours in x back to back (their
+        // halo columns meet in L2)
+        const int nedge = strips < 2 ? strips : 2;
+        const long long edge_items = static_cast<long long>(nedge) * bands * a.n_images;
+        long long img;
+        int band, strip;
+        if (item < edge_items) {
+            const long long q = item / nedge;
+            strip = (item - q * nedge) ? strips - 1 : 0;
+            img = q / bands;
+            band = static_cast<int>(q - img * bands);
+        } else {
+            const int inner = strips - 2;
+            const long long q = (item - edge_items) / inner;
+            strip = 1 + static_cast<int>((item - edge_items) - q * inner);
+            img = q / bands;
+            band = static_cast<int>(q - img * bands);
+        }
         const int x0 = strip * TW;
         if (x0 + TW <= Xlo) continue;                   // strip entirely left of the stored region (VALID)
         const int Y0 = Ylo + band * kBand;
@@ -120,40 +197,43 @@ __global__ void __launch_bounds__(kWarps * 32, RX >= 4 ? SG2D_MINB : SG2D_MINB2)
         float* vout = a.out + img * a.out_image_pitch - static_cast<long long>(a.cy) * a.out_stride - a.cx;
 
         // ---- staging of input rows ----
-        // Interior items (no boundary rule needed in x or y -- all but the first/last band and strip)
-        // stage a row with one pointer increment and one or two unconditional 16-byte copies per lane;
-        // edge items go through the generic mapped path.
-        const bool y_in = (Y0 - N >= 0) && (Y0 - N + steps <= a.rows);
+        // Strips that need no boundary rule in x (all but the first / last one) stage a row with one or
+        // two unconditional 16-byte copies per lane; interior bands advance a running source pointer,
+        // the first / last band maps the row index (clamp / reflect).  Edge strips go through the
+        // generic per-chunk path.
+        const int steps2 = (steps + 1) & ~1;   // rows are consumed two per step, see below
+        const bool y_in = (Y0 - N >= 0) && (Y0 - N + steps2 <= a.rows);
         const bool x_in = (x0 - PADX >= 0) && (x0 + TW + PADX <= a.cols);
-        const bool fast_item = y_in && x_in;
         float* const ring_lane = &ring[0][0] + 4 * lane;
-        // this lane's first chunk of the NEXT row to stage (valid for fast items)
+        const unsigned ring_lane_s = static_cast<unsigned>(__cvta_generic_to_shared(ring_lane));
+        // this lane's first chunk of the NEXT row to stage (interior items)
         const float* src_next = in + static_cast<long long>(Y0 - N) * a.in_stride + (x0 - PADX) + 4 * lane;
-        auto stage_generic = [&](int t) {
-            const int iy = map_index(Y0 - N + t, a.rows, a.boundary);
-            const float* src = in + static_cast<long long>(iy) * a.in_stride;
-            float* dst = ring[t & (kRing - 1)];
-            const int xb = x0 - PADX;
-#pragma unroll 1
-            for (int c = lane; c < ROWCH; c += 32) {
-                const int xin = xb + 4 * c;
-                if (xin >= 0 && xin + 3 < a.cols) {
-                    cp_async16(dst + 4 * c, src + xin);
+        const float* const xbase = in + (x0 - PADX) + 4 * lane;
+        // Rows t, t+1 (t even) go to ring slots t mod 8 and the next one.  Strips that need no boundary
+        // rule in x (all but the first / last): two or three unconditional 16-byte copies per row from a
+        // running source pointer (interior bands) or from the rows the boundary rule designates (first /
+        // last band).  Edge strips take the out-of-line per-chunk path.
+        auto stage_pair = [&](int t) {
+            const int slot = t & (kRing - 1);
+            if (x_in) {
+                const float *s0, *s1;
+                if (y_in) {
+                    s0 = src_next;
+                    s1 = s0 + a.in_stride;
+                    src_next = s1 + a.in_stride;
                 } else {
-#pragma unroll 1
-                    for (int e = 0; e < 4; ++e) cp_async4(dst + 4 * c + e, src + map_index(xin + e, a.cols, a.boundary));
+                    s0 = xbase + static_cast<long long>(map_index(Y0 - N + t, a.rows, a.boundary)) * a.in_stride;
+                    s1 = xbase + static_cast<long long>(map_index(Y0 - N + t + 1, a.rows, a.boundary)) * a.in_stride;
                 }
-            }
-        };
-        auto stage_row = [&](int t) {
-            if (fast_item) {
-                float* dst = ring_lane + (t & (kRing - 1)) * ROWF;
+                const unsigned d = ring_lane_s + slot * (ROWF * 4);
 #pragma unroll
                 for (int c0 = 0; c0 < ROWCH; c0 += 32)
-                    if (c0 + 32 <= ROWCH || lane < ROWCH - c0) cp_async16(dst + 4 * c0, src_next + 4 * c0);
-                src_next += a.in_stride;
+                    if (c0 + 32 <= ROWCH || lane < ROWCH - c0) {
+                        cp_async16_s(d + 16 * c0, s0 + 4 * c0);
+                        cp_async16_s(d + ROWF * 4 + 16 * c0, s1 + 4 * c0);
+                    }
             } else {
-                stage_generic(t);
+                stage_mapped(ring[slot], in, Y0 - N + t, x0 - PADX, a.rows, a.cols, a.in_stride, a.boundary, ROWF, lane);
             }
         };
         // store side, hoisted: this lane's columns, whether they lie inside the stored region and
@@ -168,24 +248,24 @@ __global__ void __launch_bounds__(kWarps * 32, RX >= 4 ? SG2D_MINB : SG2D_MINB2)
         // column weight (a uniform register that has to be re-loaded each step, 46 weights do not fit
         // the uniform register file next to everything else) is used for both rows.  An odd row count
         // is padded with one extra (boundary-mapped) row whose contributions are never emitted.
-        const int steps2 = (steps + 1) & ~1;
         __syncwarp();  // the previous item's last reads of the ring are done
 #pragma unroll 1
         for (int t = 0; t < kAhead; t += 2) {
-            if (t < steps2) { stage_row(t); stage_row(t + 1); }
+            if (t < steps2) stage_pair(t);
             cp_async_commit();
         }
 
-        // acc[jp][i]: output row (block base - 2n + i) of the column pair (2jp, 2jp+1) of this lane
+        // acc[jp][i]: partially accumulated output rows of the column pair (2jp, 2jp+1) of this lane.
+        //   RING:  output row y (band-local, y = t - wy) lives in slot (y mod NA), NA = 2n+2; the main loop
+        //          is unrolled over a full period of the ring (n+1 steps), so every index is static and
+        //          no register ever moves.
+        //   else:  slot i = output row (block base - 2n + i); blocks of kU rows end with a register shift.
         float2 acc[RX / 2][NA];
 #pragma unroll
         for (int jp = 0; jp < RX / 2; ++jp)
 #pragma unroll
             for (int i = 0; i < NA; ++i) acc[jp][i] = make_float2(0.f, 0.f);
 
-        // ROW PASS of the staged row t -> hp[r][jp] = (H_r at column 2jp, H_r at column 2jp+1).  The folded
-        // sums s_k = x[c+k] +/- x[c-k] are shared by the R row factors; the weighted sums run packed
-        // over column pairs (weight broadcast).
         auto row_pass = [&](int t, float2 (&hp)[R][RX / 2]) {
             float xs[NV * VW];
             const float* rowp = ring_lane + (t & (kRing - 1)) * ROWF + (RX - 4) * lane;
@@ -228,66 +308,147 @@ __global__ void __launch_bounds__(kWarps * 32, RX >= 4 ? SG2D_MINB : SG2D_MINB2)
                     *reinterpret_cast<float2*>(dst_row) = v[0];
                 }
             } else {
-#pragma unroll
-                for (int j = 0; j < RX; ++j)
-                    if (X + j >= Xlo && X + j < Xhi) dst_row[j] = (j & 1) ? v[j / 2].y : v[j / 2].x;
+                emit_ragged<RX>(dst_row, v, X, Xlo, Xhi);
             }
             dst_row += a.out_stride;
         };
 
+        if constexpr (RING) {
+            // The loop over steps stays rolled (one copy of the staging and row-pass code); only the column
+            // pass exists once per phase of the ring, selected by a switch.  A fully unrolled period
+            // (n+1 steps) measured 59 KB of loop body: more than the 32 KB instruction cache, the warps
+            // of an SM are spread over the whole body and stall on instruction fetch.
+            int phase = 0;
 #pragma unroll 1
-        for (int tb = 0; tb * kU < steps2; ++tb) {
-#pragma unroll
-            for (int u = 0; u < kU; u += 2) {
-                const int t = tb * kU + u;
-                if (t < steps2) {
-                    cp_async_wait<kAhead / 2 - 1>();   // rows t and t+1 have landed (this lane's part) ...
-                    __syncwarp();                      // ... and everybody else's; rows t-2, t-1 are fully consumed
-                    if (t + kAhead < steps2) { stage_row(t + kAhead); stage_row(t + kAhead + 1); }   // into their slots
-                    cp_async_commit();
+            for (int t = 0; t < steps2; t += 2) {
+                cp_async_wait<kAhead / 2 - 1>();   // rows t and t+1 have landed (this lane's part) ...
+                __syncwarp();                      // ... and everybody else's; rows t-2, t-1 are fully consumed
+                if (t + kAhead < steps2) stage_pair(t + kAhead);   // into the slots of rows t-2, t-1
+                cp_async_commit();
 
-                    float2 h0[R][RX / 2], h1[R][RX / 2];
-                    row_pass(t, h0);
-                    row_pass(t + 1, h1);
+                float2 h0[R][RX / 2], h1[R][RX / 2];
+                row_pass(t, h0);
+                row_pass(t + 1, h1);
 
-                    // ---- column pass: scatter both rows into the output rows in flight ----
-                    // row t is window row wy of output i = u + 2n - wy; row t+1 is window row wy of output i+1
+                static_switch<NA / 2>(phase, [&](auto sc) {
+                    constexpr int s2 = 2 * decltype(sc)::value;   // ring position of row t
+                    // column pass: row t is window row wy of output row t - wy -> slot (s2 - wy) mod NA, row
+                    // t+1 of the slot after it.  wy = 0 opens a new output row (plain product: the slot
+                    // still holds the row stored 2n+2 rows ago).
 #pragma unroll
                     for (int wy = 0; wy <= 2 * N; ++wy)
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
                             const float cw = w.col[r][wy];
-                            const int i = u + 2 * N - wy;
+                            constexpr int kOff = 4 * NA;   // keeps the modulo argument positive
+                            const int i0 = (s2 - wy + kOff) % NA, i1 = (s2 + 1 - wy + kOff) % NA;
 #pragma unroll
                             for (int jp = 0; jp < RX / 2; ++jp) {
-                                acc[jp][i] = __ffma2_rn(make_float2(cw, cw), h0[r][jp], acc[jp][i]);
-                                acc[jp][i + 1] = __ffma2_rn(make_float2(cw, cw), h1[r][jp], acc[jp][i + 1]);
+                                if (wy == 0 && r == 0) {
+                                    acc[jp][i0] = __fmul2_rn(make_float2(cw, cw), h0[r][jp]);
+                                    acc[jp][i1] = __fmul2_rn(make_float2(cw, cw), h1[r][jp]);
+                                } else {
+                                    acc[jp][i0] = __ffma2_rn(make_float2(cw, cw), h0[r][jp], acc[jp][i0]);
+                                    acc[jp][i1] = __ffma2_rn(make_float2(cw, cw), h1[r][jp], acc[jp][i1]);
+                                }
                             }
                         }
-
-                    // ---- output rows u and u+1 of the block are complete ----
+                    // output rows t - 2n and t + 1 - 2n are complete
                     if (t >= 2 * N && t - 2 * N < nrows) {
                         float2 v[RX / 2];
 #pragma unroll
-                        for (int jp = 0; jp < RX / 2; ++jp) v[jp] = acc[jp][u];
+                        for (int jp = 0; jp < RX / 2; ++jp) v[jp] = acc[jp][(s2 + 2) % NA];
                         emit(v);
                     }
                     if (t + 1 >= 2 * N && t + 1 - 2 * N < nrows) {
                         float2 v[RX / 2];
 #pragma unroll
-                        for (int jp = 0; jp < RX / 2; ++jp) v[jp] = acc[jp][u + 1];
+                        for (int jp = 0; jp < RX / 2; ++jp) v[jp] = acc[jp][(s2 + 3) % NA];
                         emit(v);
                     }
-                }
+                });
+                phase = phase + 1 == NA / 2 ? 0 : phase + 1;
             }
-            // block done: drop the kU completed rows
+        } else {
+#pragma unroll 1
+            for (int tb = 0; tb * kU < steps2; ++tb) {
 #pragma unroll
-            for (int jp = 0; jp < RX / 2; ++jp)
+                for (int u = 0; u < kU; u += 2) {
+                    const int t = tb * kU + u;
+                    if (t < steps2) {
+                        cp_async_wait<kAhead / 2 - 1>();   // rows t and t+1 have landed (this lane's part) ...
+                        __syncwarp();                      // ... and everybody else's; rows t-2, t-1 are fully consumed
+                        if (t + kAhead < steps2) stage_pair(t + kAhead);   // into the slots of rows t-2, t-1
+                        cp_async_commit();
+
+                        float2 h0[R][RX / 2], h1[R][RX / 2];
+                        row_pass(t, h0);
+                        row_pass(t + 1, h1);
+
+                        // ---- column pass: scatter both rows into the output rows in flight ----
+                        // row t is window row wy of output i = u + 2n - wy; row t+1 is window row wy of output i+1
 #pragma unroll
-                for (int i = 0; i < NA; ++i) acc[jp][i] = (i + kU < NA) ? acc[jp][i + kU] : make_float2(0.f, 0.f);
+                        for (int wy = 0; wy <= 2 * N; ++wy)
+#pragma unroll
+                            for (int r = 0; r < R; ++r) {
+                                const float cw = w.col[r][wy];
+                                const int i = u + 2 * N - wy;
+#pragma unroll
+                                for (int jp = 0; jp < RX / 2; ++jp) {
+                                    acc[jp][i] = __ffma2_rn(make_float2(cw, cw), h0[r][jp], acc[jp][i]);
+                                    acc[jp][i + 1] = __ffma2_rn(make_float2(cw, cw), h1[r][jp], acc[jp][i + 1]);
+                                }
+                            }
+
+                        // ---- output rows u and u+1 of the block are complete ----
+                        if (t >= 2 * N && t - 2 * N < nrows) {
+                            float2 v[RX / 2];
+#pragma unroll
+                            for (int jp = 0; jp < RX / 2; ++jp) v[jp] = acc[jp][u];
+                            emit(v);
+                        }
+                        if (t + 1 >= 2 * N && t + 1 - 2 * N < nrows) {
+                            float2 v[RX / 2];
+#pragma unroll
+                            for (int jp = 0; jp < RX / 2; ++jp) v[jp] = acc[jp][u + 1];
+                            emit(v);
+                        }
+                    }
+                }
+                // block done: drop the kU completed rows
+#pragma unroll
+                for (int jp = 0; jp < RX / 2; ++jp)
+#pragma unroll
+                    for (int i = 0; i < NA; ++i) acc[jp][i] = (i + kU < NA) ? acc[jp][i + kU] : make_float2(0.f, 0.f);
+            }
         }
         cp_async_wait<0>();
     }
+}
+
+// Ticket counters of the launches in flight: a ring of slots per device; every launch takes the next
+// slot and zeroes it in stream order.  A slot is reused after kSlots further launches on the device.
+cudaError_t next_counter(cudaStream_t stream, unsigned** out)
+{
+    constexpr unsigned kSlots = 4096;
+    static std::mutex mu;
+    static unsigned* base[64] = {};
+    static unsigned next[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    unsigned* slot;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!base[dev]) {
+            e = cudaMalloc(&base[dev], kSlots * sizeof(unsigned));
+            if (e != cudaSuccess) return e;
+        }
+        slot = base[dev] + (next[dev]++ % kSlots);
+    }
+    *out = slot;
+    return cudaMemsetAsync(slot, 0, sizeof(unsigned), stream);
 }
 
 template <int N, int R>
@@ -327,6 +488,9 @@ cudaError_t launch_nr(const Args2D& a, const SepPlan& plan, cudaStream_t stream)
     const long long bands = (a.out_rows + band - 1) / band;
     const long long items = strips * bands * a.n_images;
     if (items <= 0) return cudaSuccess;
+    if (items >= (1LL << 31)) return cudaErrorInvalidValue;
+    cudaError_t ec = next_counter(stream, &aa.counter);
+    if (ec != cudaSuccess) return ec;
     long long grid = static_cast<long long>(sms) * bps;
     const long long need = (items + kWarps - 1) / kWarps;
     if (grid > need) grid = need;
