@@ -45,8 +45,8 @@ WORKLOADS = {
                     "n-sample halo exchange between ring neighbours"),
     "c5": dict(kind="stream", rows=1 << 20, length=1024, n=10, m=2, d=1, dt=1.0, boundary="polynomial",
                desc="multichannel stream: 1,048,576 channels x 1,024-sample chunks per GPU, half_window=10 poly_order=2 derivative=1"),
-    "c4": dict(kind="2d", images=64, rows=4096, cols=4096, nx=7, ny=7, order=3, boundary="constant",
-               desc="savgol2d: 64 images of 4096x4096 per GPU, 15x15 window, order 3, constant boundary"),
+    "c4": dict(kind="2d", images=256, rows=4096, cols=4096, nx=7, ny=7, order=3, boundary="constant",
+               desc="savgol2d: 256 images of 4096x4096 per GPU, 15x15 window, order 3, constant boundary"),
 }
 
 

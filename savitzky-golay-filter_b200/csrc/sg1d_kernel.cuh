@@ -98,6 +98,38 @@ __device__ __forceinline__ float virtual_sample(const Args1D& a, const char* xro
     return p ? *p : 0.0f;
 }
 
+// Contiguous row that is not 16-byte aligned (odd pitch, offset view): lane-consecutive 4-byte copies,
+// i.e. every copy instruction still covers one contiguous 128-byte run.  Element e = lane + 32 i lives
+// at float position e + 4 (e >> 5) = lane + 36 i of the padded buffer; it is copied when lo <= 32 i < hi
+// (bounds already relative to the lane).  Out of line, like store_scalar below: these paths are fully
+// unrolled and must not cost the aligned path registers.
+template <int NE>
+__device__ __noinline__ void stage_unaligned(float* d, const char* s, int lo, int hi)
+{
+#pragma unroll
+    for (int i = 0; i < NE; ++i)
+        if (32 * i >= lo && 32 * i < hi) cp_async4(d + 36 * i, s + 128 * i);
+}
+
+// Lane-interleaved scalar stores of a parked segment (ragged last segment, misaligned or strided rows):
+// output f = lane + 32 i is parked at float position lane + 36 i; it is stored when 32 i < lim.
+static __device__ __noinline__ void store_scalar(const float* srcf, char* dst, long long stride, int lim)
+{
+    if (stride == 4) {
+        float* d = reinterpret_cast<float*>(dst);
+#pragma unroll
+        for (int i = 0; i < kR; ++i)
+            if (32 * i < lim) d[32 * i] = srcf[36 * i];
+    } else {
+        const long long step = 32 * stride;
+#pragma unroll 4
+        for (int i = 0; i < kR; ++i) {
+            if (32 * i < lim) *reinterpret_cast<float*>(dst) = srcf[36 * i];
+            dst += step;
+        }
+    }
+}
+
 // Stage one segment (kSeg outputs of one row, plus halo) into a warp's buffer: shared position 4c
 // <-> x index o0 - PAD + 4c.  Everything is asynchronous (cp.async), so no lane waits on a global
 // load here:
@@ -129,18 +161,8 @@ __device__ __forceinline__ void stage_segment(float4* dst0 /* buf + lane + (lane
             if (c >= c_lo && c < c_hi) cp_async16(dst0 + 36 * it, s + 512 * it);
         }
     } else if (a.in_stride == 4) {
-        // contiguous row that is not 16-byte aligned (odd pitch, offset view): lane-consecutive 4-byte
-        // copies, i.e. every copy instruction still covers one contiguous 128-byte run.  Element
-        // e = lane + 32 i lives at float position e + 4 (e >> 5) = lane + 36 i of the padded buffer.
         constexpr int NE = (4 * ((kSeg + 2 * N + DELTA + 3) / 4) + 31) / 32;
-        float* d = reinterpret_cast<float*>(buf) + lane;
-        const char* s = src0 + 4 * lane;
-        const int e_lo = 4 * c_lo, e_hi = 4 * c_hi;
-#pragma unroll
-        for (int i = 0; i < NE; ++i) {
-            const int e = lane + 32 * i;
-            if (e >= e_lo && e < e_hi) cp_async4(d + 36 * i, s + 128 * i);
-        }
+        stage_unaligned<NE>(reinterpret_cast<float*>(buf) + lane, src0 + 4 * lane, 4 * c_lo - lane, 4 * c_hi - lane);
     } else {
         const long long st = a.in_stride;
 #pragma unroll 1
@@ -407,23 +429,7 @@ __global__ void __launch_bounds__(kThreads, SG_MIN_BLOCKS) sg1d_kernel(const __g
             for (int i = 0; i < kR / 4; ++i) st_cs_f4(dst + 128 * i, src[36 * i]);  // chunk lane + 32 i
         } else {
             const int lim = remain < kSeg ? static_cast<int>(remain) : kSeg;
-            // lane-interleaved scalar stores (ragged last segment, misaligned or strided rows): output
-            // f = lane + 32 i of the segment is parked at float position f + 4 (f >> 5) = lane + 36 i
-            const float* srcf = reinterpret_cast<const float*>(buf_cur) + lane;
-            if (a.out_stride == 4) {
-                float* dst = reinterpret_cast<float*>(orow) + o0 + lane;
-#pragma unroll
-                for (int i = 0; i < kR; ++i)
-                    if (lane + 32 * i < lim) dst[32 * i] = srcf[36 * i];
-            } else {
-                char* dst = orow + (o0 + lane) * a.out_stride;
-                const long long step = 32 * a.out_stride;
-#pragma unroll 4
-                for (int i = 0; i < kR; ++i) {
-                    if (lane + 32 * i < lim) *reinterpret_cast<float*>(dst) = srcf[36 * i];
-                    dst += step;
-                }
-            }
+            store_scalar(reinterpret_cast<const float*>(buf_cur) + lane, orow + (o0 + lane) * a.out_stride, a.out_stride, lim - lane);
         }
         __syncwarp();  // all lanes are done with buf_cur and s_edge[warp] before the refill
         row = nrow; o0 = no0; xrow = nxrow; t = nt;

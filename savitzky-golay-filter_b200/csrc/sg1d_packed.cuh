@@ -24,7 +24,7 @@ __host__ __device__ constexpr int packed_slot_chunks(int n, int delta, int g)
 }
 
 template <int N, bool LEAD2N>
-__global__ void __launch_bounds__(kThreads, 4) sg1d_packed_kernel(const __grid_constant__ W1D W, const __grid_constant__ Args1D a)
+__global__ void __launch_bounds__(kThreads, N <= 18 ? 4 : 3) sg1d_packed_kernel(const __grid_constant__ W1D W, const __grid_constant__ Args1D a)
 {
     constexpr int LEAD = LEAD2N ? 2 * N : N;
     constexpr int PAD = Geo<LEAD>::PAD;

@@ -109,31 +109,41 @@ __device__ __forceinline__ void cp_async16_s(unsigned smem_dst, const void* gsrc
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 
-// Rows y, y+1 of an edge item (first / last band or strip) into two consecutive ring slots: the row
-// index goes through the boundary rule, chunks that exist are copied 16 bytes at a time, pad columns
-// element by element from the column the rule maps them to.  Out of line: 1/16 of the items of a 4096^2
-// image take it, it must not bloat the main loop.
-__device__ __noinline__ void stage_mapped(float* dst, const float* in, int y, int xb, int rows, int cols, long long stride,
-                                          int boundary, int rowf, int lane)
+__device__ __forceinline__ void cp_async4_s(unsigned smem_dst, const void* gsrc)
 {
-#pragma unroll 1
-    for (int rr = 0; rr < 2; ++rr, dst += rowf) {
-        const float* src = in + static_cast<long long>(map_index(y + rr, rows, boundary)) * stride;
-#pragma unroll 1
-        for (int c = lane; 4 * c < rowf; c += 32) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+
+// Two rows of an EDGE STRIP (first / last strip of the image) into two consecutive ring slots: chunks
+// that lie inside the image are copied 16 bytes at a time, pad columns element by element from the
+// column the boundary rule maps them to.  r0 / r1 = start of the (already mapped) source rows, d = this
+// lane's shared address in the first slot, xb = image column of the slot's first float.  Out of line:
+// 1/16 of the items of a 4096^2 image take it, it must not bloat the main loop.
+template <int ROWCH, int ROWF>
+__device__ __noinline__ void stage_edge_pair(unsigned d, const float* r0, const float* r1, int xb, int cols, int boundary, int lane)
+{
+#pragma unroll
+    for (int c0 = 0; c0 < ROWCH; c0 += 32) {
+        const int c = c0 + lane;
+        if (c0 + 32 <= ROWCH || c < ROWCH) {
             const int xin = xb + 4 * c;
             if (xin >= 0 && xin + 3 < cols) {
-                cp_async16(dst + 4 * c, src + xin);
+                cp_async16_s(d + 16 * c0, r0 + xin);
+                cp_async16_s(d + ROWF * 4 + 16 * c0, r1 + xin);
             } else {
-#pragma unroll 1
-                for (int e = 0; e < 4; ++e) cp_async4(dst + 4 * c + e, src + map_index(xin + e, cols, boundary));
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int m = map_index(xin + e, cols, boundary);
+                    cp_async4_s(d + 16 * c0 + 4 * e, r0 + m);
+                    cp_async4_s(d + ROWF * 4 + 16 * c0 + 4 * e, r1 + m);
+                }
             }
         }
     }
 }
 
 template <int N, int R, int RX>
-__global__ void __launch_bounds__(kWarps * 32, RX >= 4 ? SG2D_MINB : SG2D_MINB2) sep_kernel(const __grid_constant__ SepW<R> w,
+__global__ void __launch_bounds__(kWarps * 32, RX >= 4 ? ((N <= 6 || (N == 7 && (R == 2 || R == 3))) ? SG2D_MINB : 3) : SG2D_MINB2) sep_kernel(const __grid_constant__ SepW<R> w,
                                                                             const __grid_constant__ Args2D a)
 {
     constexpr int TW = 32 * RX;                 // output columns per strip
@@ -233,7 +243,10 @@ __global__ void __launch_bounds__(kWarps * 32, RX >= 4 ? SG2D_MINB : SG2D_MINB2)
                         cp_async16_s(d + ROWF * 4 + 16 * c0, s1 + 4 * c0);
                     }
             } else {
-                stage_mapped(ring[slot], in, Y0 - N + t, x0 - PADX, a.rows, a.cols, a.in_stride, a.boundary, ROWF, lane);
+                stage_edge_pair<ROWCH, ROWF>(ring_lane_s + slot * (ROWF * 4),
+                                             in + static_cast<long long>(map_index(Y0 - N + t, a.rows, a.boundary)) * a.in_stride,
+                                             in + static_cast<long long>(map_index(Y0 - N + t + 1, a.rows, a.boundary)) * a.in_stride,
+                                             x0 - PADX, a.cols, a.boundary, lane);
             }
         };
         // store side, hoisted: this lane's columns, whether they lie inside the stored region and
