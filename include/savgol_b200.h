@@ -302,6 +302,14 @@ size_t savgol_mcstream_samples_output(const SavgolMCStream *s);   /* per channel
  * checkpointing. */
 float *savgol_mcstream_state(SavgolMCStream *s, size_t *n_floats);
 
+/* Checkpoint / resume of a long-running stream (host blob: counters + carry state).
+ * save() returns the bytes written (== checkpoint_size) or -1; restore() returns 0, or -1
+ * when the blob was written by a stream with another configuration / channel count.
+ * A restored stream continues bit-identically to the one that was saved. */
+size_t savgol_mcstream_checkpoint_size(const SavgolMCStream *s);
+long long savgol_mcstream_save(SavgolMCStream *s, void *blob, size_t capacity);
+int savgol_mcstream_restore(SavgolMCStream *s, const void *blob, size_t bytes);
+
 #ifdef __cplusplus
 }
 #endif

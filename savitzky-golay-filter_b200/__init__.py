@@ -279,6 +279,19 @@ class SavgolMCStream:
     def reset(self):
         lib().savgol_mcstream_reset(self._h)
 
+    def save(self) -> bytes:
+        """Checkpoint (counters + per-channel carry state) as a host blob."""
+        n = int(lib().savgol_mcstream_checkpoint_size(self._h))
+        buf = C.create_string_buffer(n)
+        if lib().savgol_mcstream_save(self._h, buf, n) != n:
+            raise RuntimeError("savgol_mcstream_save failed")
+        return buf.raw
+
+    def restore(self, blob: bytes):
+        """Resume from a blob written by save() of a stream with the same configuration."""
+        if lib().savgol_mcstream_restore(self._h, blob, len(blob)) != 0:
+            raise ValueError("savgol_mcstream_restore: checkpoint does not match this stream")
+
     @property
     def latency(self):
         return int(lib().savgol_mcstream_latency(self._h))

@@ -106,6 +106,9 @@ PROTOTYPES = {
     "savgol_mcstream_samples_received": (C.c_size_t, [C.c_void_p]),
     "savgol_mcstream_samples_output": (C.c_size_t, [C.c_void_p]),
     "savgol_mcstream_state": (f32p, [C.c_void_p, C.POINTER(C.c_size_t)]),
+    "savgol_mcstream_checkpoint_size": (C.c_size_t, [C.c_void_p]),
+    "savgol_mcstream_save": (C.c_longlong, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "savgol_mcstream_restore": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
 }
 
 _lib = None

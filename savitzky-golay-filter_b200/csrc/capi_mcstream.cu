@@ -267,6 +267,54 @@ size_t savgol_mcstream_channels(const SavgolMCStream* s) { return s ? s->channel
 size_t savgol_mcstream_latency(const SavgolMCStream* s) { return s ? static_cast<size_t>(s->n) : 0; }
 size_t savgol_mcstream_samples_received(const SavgolMCStream* s) { return s ? s->received : 0; }
 size_t savgol_mcstream_samples_output(const SavgolMCStream* s) { return s ? s->emitted : 0; }
+// Checkpoint blob: header + the carry state.  Plain host memory, self-describing, so a stream can be
+// resumed in another process / on another GPU (same configuration and channel count).
+struct McCheckpoint {
+    unsigned magic, version;
+    unsigned long long channels, received, emitted;
+    int n, ws;
+};
+constexpr unsigned kCkptMagic = 0x53474d43u;  // "SGMC"
+
+size_t savgol_mcstream_checkpoint_size(const SavgolMCStream* s)
+{
+    return s ? sizeof(McCheckpoint) + s->channels * static_cast<size_t>(s->ws) * sizeof(float) : 0;
+}
+
+long long savgol_mcstream_save(SavgolMCStream* s, void* blob, size_t capacity)
+{
+    const size_t need = savgol_mcstream_checkpoint_size(s);
+    if (!s || !blob || capacity < need) return -1;
+    McCheckpoint h{kCkptMagic, 1u, s->channels, s->received, s->emitted, s->n, s->ws};
+    std::memcpy(blob, &h, sizeof h);
+    cudaStream_t st = sge::current_stream();
+    if (!cuda_ok(cudaMemcpyAsync(static_cast<char*>(blob) + sizeof h, s->state[s->cur], need - sizeof h, cudaMemcpyDeviceToHost, st),
+                 "checkpoint D2H") ||
+        !cuda_ok(cudaStreamSynchronize(st), "sync"))
+        return -1;
+    return static_cast<long long>(need);
+}
+
+int savgol_mcstream_restore(SavgolMCStream* s, const void* blob, size_t bytes)
+{
+    if (!s || !blob || bytes < sizeof(McCheckpoint)) return -1;
+    McCheckpoint h;
+    std::memcpy(&h, blob, sizeof h);
+    if (h.magic != kCkptMagic || h.version != 1u || h.channels != s->channels || h.n != s->n || h.ws != s->ws ||
+        bytes < savgol_mcstream_checkpoint_size(s)) {
+        std::fprintf(stderr, "savgol_mcstream_restore: checkpoint does not match this stream\n");
+        return -1;
+    }
+    cudaStream_t st = sge::current_stream();
+    if (!cuda_ok(cudaMemcpyAsync(s->state[s->cur], static_cast<const char*>(blob) + sizeof h, bytes - sizeof h, cudaMemcpyHostToDevice, st),
+                 "checkpoint H2D") ||
+        !cuda_ok(cudaStreamSynchronize(st), "sync"))
+        return -1;
+    s->received = static_cast<size_t>(h.received);
+    s->emitted = static_cast<size_t>(h.emitted);
+    return 0;
+}
+
 float* savgol_mcstream_state(SavgolMCStream* s, size_t* n_floats)
 {
     if (!s) return nullptr;

@@ -94,3 +94,31 @@ def test_config5_shape_channels(oracle):
     f = sg.SavgolFilter(10, 2, 1, 1.0, "polynomial")
     yb = f.apply(torch.from_numpy(sig[pick]).cuda()).cpu().numpy()
     assert np.max(np.abs(yb - got[pick])) <= 1e-6 * float(np.abs(sig).max())
+
+
+def test_checkpoint_resume_is_bit_identical():
+    # save after a few chunks, resume in a fresh stream: same outputs as the uninterrupted stream
+    rng = np.random.default_rng(9)
+    C_, n = 53, 7
+    sig = rng.standard_normal((C_, 3000)).astype(np.float32)
+    d = torch.from_numpy(sig).cuda()
+    a = sg.SavgolMCStream(C_, n, 3, 1, 0.5)
+    outs = []
+    for lo, hi in ((0, 5), (5, 700), (700, 1500)):
+        o, k = a.push(d[:, lo:hi].contiguous())
+        outs.append(o[:, :k].cpu().numpy())
+    blob = a.save()
+    rest_a = [a.push(d[:, 1500:2200].contiguous()), a.push(d[:, 2200:].contiguous())]
+    fa, ka = a.flush(d)
+    b = sg.SavgolMCStream(C_, n, 3, 1, 0.5)
+    b.restore(blob)
+    assert b.samples_received == 1500 and b.samples_output == 1500 - n
+    rest_b = [b.push(d[:, 1500:2200].contiguous()), b.push(d[:, 2200:].contiguous())]
+    fb, kb = b.flush(d)
+    for (oa, ka_), (ob, kb_) in zip(rest_a, rest_b):
+        assert ka_ == kb_ and torch.equal(oa[:, :ka_], ob[:, :kb_])
+    assert ka == kb == n and torch.equal(fa[:, :n], fb[:, :n])
+    # a blob from another configuration is refused
+    c = sg.SavgolMCStream(C_, n + 1, 3, 1, 0.5)
+    with pytest.raises(ValueError):
+        c.restore(blob)
