@@ -471,9 +471,14 @@ cudaError_t launch_nr(const Args2D& a, const SepPlan& plan, cudaStream_t stream)
     SepW<R> w;
     const float sc = a.scale;
     for (int r = 0; r < R; ++r) {
-        w.rc[r] = plan.row[r][N];
-        for (int k = 1; k <= N; ++k) w.rk[r][k - 1] = plan.row[r][N + k];
-        for (int k = 0; k <= 2 * N; ++k) w.col[r][k] = plan.col[r][k] * sc;
+        // N = max(nx, ny): the shorter factor is centred and zero-padded (the extra taps multiply
+        // boundary-mapped, i.e. finite, samples by 0)
+        w.rc[r] = plan.row[r][plan.nx];
+        for (int k = 1; k <= N; ++k) w.rk[r][k - 1] = k <= plan.nx ? plan.row[r][plan.nx + k] : 0.0f;
+        for (int k = 0; k <= 2 * N; ++k) {
+            const int j = k - N + plan.ny;
+            w.col[r][k] = (j >= 0 && j <= 2 * plan.ny) ? plan.col[r][j] * sc : 0.0f;
+        }
     }
     w.sx = plan.parity_x < 0 ? -1.0f : 1.0f;
     auto kern = sep_kernel<N, R, RX>;
@@ -526,11 +531,12 @@ cudaError_t launch_n(const Args2D& a, const SepPlan& plan, cudaStream_t stream)
 
 }  // namespace
 
-// The streaming kernel is instantiated for square windows (nx == ny); it needs 16-byte aligned
-// rows on both sides.  Everything else runs through sg2d_direct.cu.
+// The streaming kernel is instantiated per half-window N = max(nx, ny) (a rectangular window runs with
+// its shorter factor zero-padded); it needs 16-byte aligned input rows.  Everything else runs through
+// sg2d_direct.cu.
 bool separable_supported(const Args2D& a, const SepPlan& plan)
 {
-    if (plan.rank < 1 || plan.rank > kMaxRank || plan.nx != plan.ny) return false;
+    if (plan.rank < 1 || plan.rank > kMaxRank || plan.nx < 1 || plan.ny < 1 || plan.nx > 16 || plan.ny > 16) return false;
     if ((reinterpret_cast<uintptr_t>(a.in) & 15) || (a.in_stride & 3) || (a.in_image_pitch & 3)) return false;
     if (a.rows < 1 || a.cols < 4) return false;
     return true;
@@ -538,7 +544,7 @@ bool separable_supported(const Args2D& a, const SepPlan& plan)
 
 cudaError_t launch_separable(const Args2D& a, const SepPlan& plan, cudaStream_t stream)
 {
-    switch (plan.nx) {
+    switch (plan.nx > plan.ny ? plan.nx : plan.ny) {
 #define SG2D_CASE(n) case n: return launch_n<n>(a, plan, stream);
         SG2D_CASE(1) SG2D_CASE(2) SG2D_CASE(3) SG2D_CASE(4) SG2D_CASE(5) SG2D_CASE(6) SG2D_CASE(7) SG2D_CASE(8)
         SG2D_CASE(9) SG2D_CASE(10) SG2D_CASE(11) SG2D_CASE(12) SG2D_CASE(13) SG2D_CASE(14) SG2D_CASE(15) SG2D_CASE(16)

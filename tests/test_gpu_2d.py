@@ -152,15 +152,15 @@ def test_laplacian_is_one_fused_pass(oracle):
     assert np.array_equal(bits(lap_e.cpu().numpy()), bits(want))
 
 
-@pytest.mark.parametrize("n,order,dx,dy", [(7, 3, 0, 0), (3, 2, 1, 0), (8, 4, 0, 2), (5, 5, 1, 1)])
-def test_streaming_kernel_bands_strips_and_edges(oracle, n, order, dx, dy):
+@pytest.mark.parametrize("n,ny,order,dx,dy", [(7, 7, 3, 0, 0), (3, 3, 2, 1, 0), (8, 8, 4, 0, 2), (5, 5, 5, 1, 1), (7, 2, 3, 0, 1), (2, 9, 4, 1, 0)])
+def test_streaming_kernel_bands_strips_and_edges(oracle, n, ny, order, dx, dy):
     # shapes that exercise the separable streaming kernel's work decomposition: many bands with an odd
     # last band (the padded extra row must not be read past the image), one / two / many strips, narrow
     # images whose single strip has both x edges, a batch with image pitch
     rng = np.random.default_rng(500 + n)
-    o = oracle.Filter2D(n, n, order, dx, dy)
-    f = sg.Savgol2DFilter(n, n, order, dx, dy)
-    for images, rows, cols in ((1, 1101, 1024), (1, 333, 64), (2, 97, 256), (3, 150, 132), (1, 2 * n + 2, 516)):
+    o = oracle.Filter2D(n, ny, order, dx, dy)     # (n, ny) = (half_window_x, half_window_y): rectangular windows too
+    f = sg.Savgol2DFilter(n, ny, order, dx, dy)
+    for images, rows, cols in ((1, 1101, 1024), (1, 333, 64), (2, 97, 256), (3, 150, 132), (1, 2 * ny + 2, 516)):
         x = rng.standard_normal((images, rows, cols)).astype(np.float32)
         d = torch.from_numpy(x).cuda()
         tol = 1e-6 * float(np.abs(x).max()) * o.scale
