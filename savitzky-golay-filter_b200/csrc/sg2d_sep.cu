@@ -114,9 +114,10 @@ __device__ __forceinline__ void cp_async4_s(unsigned smem_dst, const void* gsrc)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 
-// Two rows of an EDGE STRIP (first / last strip of the image) into two consecutive ring slots: chunks
-// that lie inside the image are copied 16 bytes at a time, pad columns element by element from the
-// column the boundary rule maps them to.  r0 / r1 = start of the (already mapped) source rows, d = this
+// Two rows of an EDGE STRIP (first / last strip of the image), or of an image whose rows are not 16-byte
+// aligned, into two consecutive ring slots: chunks that lie inside the image and are aligned are copied
+// 16 bytes at a time, everything else element by element (pad columns from the column the boundary rule
+// maps them to).  r0 / r1 = start of the (already mapped) source rows, d = this
 // lane's shared address in the first slot, xb = image column of the slot's first float.  Out of line:
 // 1/16 of the items of a 4096^2 image take it, it must not bloat the main loop.
 template <int ROWCH, int ROWF>
@@ -127,15 +128,16 @@ __device__ __noinline__ void stage_edge_pair(unsigned d, const float* r0, const 
         const int c = c0 + lane;
         if (c0 + 32 <= ROWCH || c < ROWCH) {
             const int xin = xb + 4 * c;
-            if (xin >= 0 && xin + 3 < cols) {
-                cp_async16_s(d + 16 * c0, r0 + xin);
-                cp_async16_s(d + ROWF * 4 + 16 * c0, r1 + xin);
-            } else {
+            const bool inside = xin >= 0 && xin + 3 < cols;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int m = map_index(xin + e, cols, boundary);
-                    cp_async4_s(d + 16 * c0 + 4 * e, r0 + m);
-                    cp_async4_s(d + ROWF * 4 + 16 * c0 + 4 * e, r1 + m);
+            for (int rr = 0; rr < 2; ++rr) {
+                const float* r = rr ? r1 : r0;
+                const unsigned dd = d + rr * (ROWF * 4) + 16 * c0;
+                if (inside && (reinterpret_cast<uintptr_t>(r + xin) & 15) == 0) {
+                    cp_async16_s(dd, r + xin);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) cp_async4_s(dd + 4 * e, r + (inside ? xin + e : map_index(xin + e, cols, boundary)));
                 }
             }
         }
@@ -162,6 +164,8 @@ __global__ void __launch_bounds__(kWarps * 32, RX >= 4 ? ((N <= 6 || (N == 7 && 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float(*ring)[ROWF] = s_ring[warp];
 
+    // 16-byte copies need aligned rows; other images take the per-chunk path for every strip
+    const bool rows_aligned = ((reinterpret_cast<uintptr_t>(a.in) & 15) | (a.in_stride & 3) | (a.in_image_pitch & 3)) == 0;
     const int Ylo = a.cy, Yhi = a.cy + a.out_rows;      // stored region in full-image coordinates
     const int Xlo = a.cx, Xhi = a.cx + a.out_cols;
     const int strips = (Xhi + TW - 1) / TW;
@@ -213,7 +217,7 @@ __global__ void __launch_bounds__(kWarps * 32, RX >= 4 ? ((N <= 6 || (N == 7 && 
         // generic per-chunk path.
         const int steps2 = (steps + 1) & ~1;   // rows are consumed two per step, see below
         const bool y_in = (Y0 - N >= 0) && (Y0 - N + steps2 <= a.rows);
-        const bool x_in = (x0 - PADX >= 0) && (x0 + TW + PADX <= a.cols);
+        const bool x_in = (x0 - PADX >= 0) && (x0 + TW + PADX <= a.cols) && rows_aligned;
         float* const ring_lane = &ring[0][0] + 4 * lane;
         const unsigned ring_lane_s = static_cast<unsigned>(__cvta_generic_to_shared(ring_lane));
         // this lane's first chunk of the NEXT row to stage (interior items)
@@ -532,12 +536,10 @@ cudaError_t launch_n(const Args2D& a, const SepPlan& plan, cudaStream_t stream)
 }  // namespace
 
 // The streaming kernel is instantiated per half-window N = max(nx, ny) (a rectangular window runs with
-// its shorter factor zero-padded); it needs 16-byte aligned input rows.  Everything else runs through
-// sg2d_direct.cu.
+// its shorter factor zero-padded).  Half-windows above 16 and the exact flavour run through sg2d_direct.cu.
 bool separable_supported(const Args2D& a, const SepPlan& plan)
 {
     if (plan.rank < 1 || plan.rank > kMaxRank || plan.nx < 1 || plan.ny < 1 || plan.nx > 16 || plan.ny > 16) return false;
-    if ((reinterpret_cast<uintptr_t>(a.in) & 15) || (a.in_stride & 3) || (a.in_image_pitch & 3)) return false;
     if (a.rows < 1 || a.cols < 4) return false;
     return true;
 }

@@ -76,6 +76,13 @@ def test_config4_window_batch_constant(oracle):
     for i in range(3):
         ref = o.apply(view[i].cpu().numpy().copy(), "constant")
         assert np.max(np.abs(out[i].cpu().numpy() - ref)) <= 1e-6
+    # a view whose rows are not 16-byte aligned takes the same kernel through its per-chunk staging path
+    view2 = big[:, 10:190, 21:321]
+    out2 = torch.zeros(3, 180, 300, device="cuda")
+    f.apply(view2, "constant", out=out2)
+    for i in range(3):
+        ref = o.apply(view2[i].cpu().numpy().copy(), "constant")
+        assert np.max(np.abs(out2[i].cpu().numpy() - ref)) <= 1e-6
     # host path == device path
     h = f.apply(view[0].cpu().numpy().copy(), "constant")
     assert np.array_equal(bits(h), bits(out[0].cpu().numpy()))
