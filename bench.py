@@ -274,7 +274,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict({"workload": wl["desc"], "l2": "inputs larger than L2 (no flush needed)" if res["bytes_in"] > 2e8
                             else "L2 flushed between steps by a 256 MiB memset", "sharding": "independent units per rank, no collective"
-                            if wl["kind"] != "long" else "contiguous slices, n-sample halo all_gather per step"}, **res.get("config", {})),
+                            if wl["kind"] != "long" else "contiguous slices of one signal per rank"}, **res.get("config", {})),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": res.get("traffic", traffic), "peak_kind": peak_kind,
                          "kernel": res["kernel"], "kernel_ms": round(kern_ms, 5), "alg_bytes_per_launch": alg_bytes},

@@ -100,10 +100,27 @@ def run_1d_family(wl, args, sg, lib, torch, np, dev, rank, world, barrier, max_o
         strip = torch.empty(2 * n, device=dev)
         allstrips = torch.empty(world * 2 * n, device=dev)
         xp, yp = x.data_ptr(), y.data_ptr()
+        ring = None
+        halo_mode = os.environ.get("SG_C3_HALO", "p2p")   # p2p: halos read from the neighbours' HBM inside the kernel
+        if world > 1:
+            strip[:n] = x[:n]
+            strip[n:] = x[L - n:]
+            dist.all_gather_into_tensor(allstrips, strip)   # the parity checker's copy of the neighbours' edges
+            if halo_mode == "p2p":
+                from savgol_b200 import dist as sgdist
+                ring = sgdist.PeerRing(x, n, True)
+                left_p, right_p = C.c_void_p(ring.left_ptr), C.c_void_p(ring.right_ptr)
+            torch.cuda.synchronize()
+            dist.barrier()
+        res.setdefault("config", {})["halo"] = ("none (one slice, periodic wrap inside the kernel)" if world == 1 else
+                                                "ring neighbours' slices mapped by CUDA IPC, 2n samples read over NVLink inside the kernel, "
+                                                "no collective per step" if ring else "NCCL all_gather of 2n floats per rank per step")
 
         def call():
             if world == 1:
                 rc = lib.savgol_apply(f.handle, xp, yp, L)  # periodic wrap inside the kernel
+            elif ring is not None:
+                rc = lib.savgol_apply_halo(f.handle, xp, yp, L, left_p, right_p)
             else:
                 # n-sample halo exchange between ring neighbours (NCCL all_gather of 2n floats per rank)
                 strip[:n] = x[:n]

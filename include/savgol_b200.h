@@ -260,6 +260,21 @@ int savgol_apply_batch(const SavgolFilter *filter, const float *input, float *ou
 int savgol_apply_halo(const SavgolFilter *filter, const float *input, float *output, size_t length,
                       const float *left_halo, const float *right_halo);
 
+/* Peer memory for the partitioned signal (one process per GPU) -------------- */
+
+/* The halo pointers of savgol_apply_halo() may point into ANOTHER GPU's memory: the kernel
+ * reads the 2n halo samples over NVLink while it stages the slice, so the "halo exchange"
+ * needs no collective and no copy.  With one process per GPU the neighbour's slice is mapped
+ * through CUDA IPC: the owner exports (handle, offset) for its slice pointer, ships the
+ * SAVGOL_B200_IPC_HANDLE_BYTES + the offset to the neighbour by any means (torch.distributed,
+ * MPI, a pipe), the neighbour opens it once and keeps the mapping for the life of the buffer.
+ * The caller orders producer and consumer (the neighbour's samples must be complete before the
+ * launch that reads them).  export/close return 0 or -1, open returns NULL on error. */
+#define SAVGOL_B200_IPC_HANDLE_BYTES 64
+int savgol_b200_ipc_export(const void *dev_ptr, void *handle64, size_t *offset);
+void *savgol_b200_ipc_open(const void *handle64, size_t offset);
+int savgol_b200_ipc_close(void *mapped, size_t offset);
+
 /* 2D batch ---------------------------------------------------------------- */
 
 /* `n_images` images, image i at input + i*in_image_pitch (elements). */

@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsavgol_b200.so")
 
 MAX_HALF_WINDOW = 32
+IPC_HANDLE_BYTES = 64   # SAVGOL_B200_IPC_HANDLE_BYTES
 MAX_WINDOW = 65
 
 f32p = C.POINTER(C.c_float)
@@ -96,6 +97,9 @@ PROTOTYPES = {
     "savgol_apply_halo": (C.c_int, [FP, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "savgol2d_apply_batch": (C.c_int, [F2, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int,
                                        C.c_size_t, C.c_size_t, C.c_int]),
+    "savgol_b200_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]),
+    "savgol_b200_ipc_open": (C.c_void_p, [C.c_void_p, C.c_size_t]),
+    "savgol_b200_ipc_close": (C.c_int, [C.c_void_p, C.c_size_t]),
     "savgol_mcstream_create": (C.c_void_p, [C.POINTER(SavgolConfig), C.c_size_t]),
     "savgol_mcstream_destroy": (None, [C.c_void_p]),
     "savgol_mcstream_reset": (None, [C.c_void_p]),

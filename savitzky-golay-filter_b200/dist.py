@@ -51,3 +51,73 @@ def apply_partitioned(filt, x_local, out=None, group=None):
     periodic = int(filt.config.boundary) == 2
     left, right = exchange_halos(x_local, filt.half_window, periodic, group)
     return filt.apply_halo(x_local, left, right, out=out)
+
+
+class PeerRing:
+    """Ring neighbours' slices of a partitioned signal, mapped into this process (CUDA IPC).
+
+    Set up once per resident buffer: every rank exports (IPC handle, offset, length) of its slice, the
+    tuples travel through one all_gather_object, each rank opens its two neighbours.  After that a
+    step needs NO communication call at all: `apply` hands savgol_apply_halo pointers into the
+    neighbours' HBM and the kernel reads the 2n halo samples over NVLink while staging the slice.
+    The caller orders producer and consumer (neighbours' samples complete before `apply`)."""
+
+    def __init__(self, x_local, half_window: int, periodic: bool, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        from . import lib
+        from ._capi import IPC_HANDLE_BYTES
+
+        self._lib = lib()
+        self.n = int(half_window)
+        self.x = x_local
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if x_local.shape[0] < self.n:
+            raise ValueError("every slice must hold at least half_window samples")
+        self._mapped = []          # (mapped pointer, offset) to close
+        self.left_ptr = self.right_ptr = None
+        if world == 1:
+            if periodic:            # the signal wraps onto itself
+                self.left_ptr = x_local.data_ptr() + 4 * (x_local.shape[0] - self.n)
+                self.right_ptr = x_local.data_ptr()
+            return
+        handle = (C.c_ubyte * IPC_HANDLE_BYTES)()
+        off = C.c_size_t(0)
+        if self._lib.savgol_b200_ipc_export(C.c_void_p(x_local.data_ptr()), handle, C.byref(off)) != 0:
+            raise RuntimeError("savgol_b200_ipc_export failed")
+        infos = [None] * world
+        dist.all_gather_object(infos, (bytes(handle), int(off.value), int(x_local.shape[0])), group=group)
+        opened = {}
+
+        def base_of(r):
+            if r not in opened:
+                h, o, _len = infos[r]
+                p = self._lib.savgol_b200_ipc_open(C.create_string_buffer(h, IPC_HANDLE_BYTES), C.c_size_t(o))
+                if not p:
+                    raise RuntimeError(f"savgol_b200_ipc_open failed for rank {r}")
+                opened[r] = int(p)
+                self._mapped.append((int(p), o))
+            return opened[r]
+
+        prev, nxt = (rank - 1) % world, (rank + 1) % world
+        if periodic or rank > 0:
+            self.left_ptr = base_of(prev) + 4 * (infos[prev][2] - self.n)
+        if periodic or rank < world - 1:
+            self.right_ptr = base_of(nxt)
+
+    def apply(self, filt, out):
+        """Filters the local slice; halos are read from the neighbours' memory inside the kernel."""
+        import ctypes as C
+        rc = self._lib.savgol_apply_halo(filt.handle, C.c_void_p(self.x.data_ptr()), C.c_void_p(out.data_ptr()), self.x.shape[0],
+                                         C.c_void_p(self.left_ptr) if self.left_ptr else None,
+                                         C.c_void_p(self.right_ptr) if self.right_ptr else None)
+        if rc != 0:
+            raise RuntimeError("savgol_apply_halo failed (see stderr)")
+        return out
+
+    def close(self):
+        import ctypes as C
+        for p, o in self._mapped:
+            self._lib.savgol_b200_ipc_close(C.c_void_p(p), C.c_size_t(o))
+        self._mapped = []
