@@ -16,6 +16,20 @@ for n, m, d in [(1, 1, 0), (7, 3, 1), (16, 3, 1), (21, 4, 2), (32, 4, 2)]:
         f.apply_valid(x)
         f.apply(x, out=x)            # in-place (scratch path)
         f.close()
+# short rows (packed kernel: 2 / 4 / 8 rows per warp), aligned and odd pitches, offset views
+for n, m, d in [(2, 2, 0), (12, 4, 0), (25, 4, 2), (32, 5, 0)]:
+    for mode in ("polynomial", "reflect", "periodic", "constant"):
+        f = sg.SavgolFilter(n, m, d, 1.0, mode)
+        for rows, L, pitch in [(7, 2 * n + 1, 2 * n + 1), (33, 128, 128), (9, 250, 253), (5, 360, 360), (17, 512, 516), (3, 100, 101)]:
+            if L < 2 * n + 1:
+                continue
+            big = torch.from_numpy(rng.standard_normal((rows, pitch + 1)).astype(np.float32)).cuda()
+            f.apply(big[:, 1:1 + L])
+            f.apply(big[:, :L])
+        # unaligned long rows (out-of-line staging / store paths)
+        big = torch.from_numpy(rng.standard_normal((3, 4099)).astype(np.float32)).cuda()
+        f.apply(big[:, 1:4098])
+        f.close()
 f = sg.SavgolFilter(5, 2, 1, 0.5)
 rec = torch.zeros(3 * 700, device="cuda")
 assert f.apply_strided(rec.data_ptr(), 12, 4, rec.data_ptr(), 12, 8, 700) == 0
@@ -23,10 +37,14 @@ s = sg.SavgolMCStream(33, 10, 2, 1, 1.0)
 for K in (5, 30, 1024, 77):
     s.push(torch.from_numpy(rng.standard_normal((33, K)).astype(np.float32)).cuda())
 s.flush(torch.empty(1, device="cuda"))
-for nx, o, dx, dy in [(2, 2, 0, 0), (7, 3, 0, 0), (7, 3, 1, 0), (12, 5, 0, 0), (16, 6, 0, 0)]:
-    f2 = sg.Savgol2DFilter(nx, nx, o, dx, dy)
+blob = s.save()
+s2 = sg.SavgolMCStream(33, 10, 2, 1, 1.0)
+s2.restore(blob)
+s2.push(torch.from_numpy(rng.standard_normal((33, 300)).astype(np.float32)).cuda())   # short chunk: packed stream kernel
+for nx, ny, o, dx, dy in [(2, 2, 2, 0, 0), (7, 7, 3, 0, 0), (7, 7, 3, 1, 0), (12, 12, 5, 0, 0), (16, 16, 6, 0, 0), (7, 3, 3, 0, 0), (2, 9, 4, 0, 1)]:
+    f2 = sg.Savgol2DFilter(nx, ny, o, dx, dy)
     for b in ("valid", "constant", "reflect"):
-        for shape in [(2 * nx + 3, 2 * nx + 9), (150, 300), (2, 70, 260)]:
+        for shape in [(2 * ny + 3, 2 * nx + 9), (150, 300), (2, 70, 260), (333, 131), (1, 600, 64)]:
             img = torch.from_numpy(rng.random(shape).astype(np.float32)).cuda()
             f2.apply(img, b)
 sg.set_exact(True)
