@@ -1,0 +1,108 @@
+"""BASELINE configs at FULL size on the GPU.  The oracle cannot cover 2.7e8 .. 4.3e9 samples in seconds, so
+each config is checked (a) over its whole output against the `exact` flavour of the same library -- which
+the other test files prove bit-identical to the reference -- within the north_star tolerance, (b) against
+the oracle on a sample of rows / crops, (c) through a size-independent property (linearity, polynomial
+reproduction)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+import savgol_b200 as sg  # noqa: E402
+
+
+@pytest.fixture(autouse=True)
+def _fast_mode():
+    sg.set_exact(False)
+    yield
+    sg.set_exact(False)
+
+
+def test_config2_full_batch(oracle):
+    rows, L, n, m, d = 65536, 4096, 16, 3, 1
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    x = torch.randn(rows, L, device="cuda", generator=g)
+    f = sg.SavgolFilter(n, m, d, 1.0, "reflect")
+    y = f.apply(x)
+    tol = 1e-6 * float(x.abs().max())
+    sg.set_exact(True)
+    ye = f.apply(x)
+    sg.set_exact(False)
+    assert float((y - ye).abs().max()) <= tol
+    pick = [0, 1, 777, 32768, 65535]
+    ref = oracle.Filter1D(n, m, d, 1.0, "reflect").apply(x[pick].cpu().numpy())
+    assert np.array_equal(ye[pick].cpu().numpy().view(np.uint32), ref.view(np.uint32))
+    # linearity over the whole batch: F(2x + 3 flip(x)) == 2 F(x) + 3 F(flip(x)) up to rounding
+    x2 = torch.flip(x, dims=[0])
+    lhs = f.apply(2.0 * x + 3.0 * x2)
+    rhs = 2.0 * y + 3.0 * torch.flip(y, dims=[0])
+    assert float((lhs - rhs).abs().max()) <= 8 * tol
+    # first derivative of a ramp is its slope everywhere (reflect pads break it only in the last n samples per side)
+    ramp = torch.arange(L, device="cuda", dtype=torch.float32).repeat(1024, 1) * 0.25
+    dr = f.apply(ramp)
+    assert float((dr[:, n:L - n] - 0.25).abs().max()) <= 1e-6 * float(ramp.max())
+
+
+def test_config3_slice_periodic_long_signal():
+    L, n = 1 << 29, 32
+    g = torch.Generator(device="cuda"); g.manual_seed(2)
+    x = torch.randn(L, device="cuda", generator=g)
+    f = sg.SavgolFilter(n, 4, 2, 1.0, "periodic")
+    y = f.apply(x)
+    sg.set_exact(True)
+    ye = f.apply(x)
+    sg.set_exact(False)
+    assert float((y - ye).abs().max()) <= 1e-6 * float(x.abs().max())
+    # periodic filtering commutes with a cyclic shift
+    s = 123_457
+    ys = f.apply(torch.roll(x, s))
+    assert torch.equal(ys, torch.roll(y, s))
+
+
+def test_config4_full_images(oracle):
+    images, rows, cols = 4, 4096, 4096        # 256 images = the same kernel over more (image, band, strip) items
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    x = torch.rand(images, rows, cols, device="cuda", generator=g)
+    f = sg.Savgol2DFilter(7, 7, 3)
+    y = f.apply(x, "constant")
+    sg.set_exact(True)
+    ye = f.apply(x, "constant")               # literal 225-tap kernel in the reference's summation order
+    sg.set_exact(False)
+    assert float((y - ye).abs().max()) <= 1e-6 * float(x.max())
+    o = oracle.Filter2D(7, 7, 3)
+    crop = x[3, :200, cols - 300:].cpu().numpy()
+    ref = o.apply(crop, "constant")
+    got = ye[3, :200 - 7, cols - 300 + 7:].cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), ref[:200 - 7, 7:].view(np.uint32))
+    # an order-3 filter reproduces cubic surfaces in the interior
+    yy, xx = torch.meshgrid(torch.arange(512, device="cuda", dtype=torch.float32), torch.arange(512, device="cuda", dtype=torch.float32), indexing="ij")
+    surf = 1e-6 * (xx ** 3) - 2e-4 * xx * yy + 0.01 * yy + 3.0
+    out = f.apply(surf, "constant")
+    assert float((out[7:-7, 7:-7] - surf[7:-7, 7:-7]).abs().max()) <= 2e-6 * float(surf.abs().max())
+
+
+def test_config5_full_channels():
+    C_, K, n = 1 << 20, 1024, 10
+    g = torch.Generator(device="cuda"); g.manual_seed(4)
+    chunks = [torch.randn(C_, K, device="cuda", generator=g) for _ in range(3)]
+
+    def run():
+        s = sg.SavgolMCStream(C_, n, 2, 1, 1.0)
+        outs = []
+        for c in chunks:
+            o, k = s.push(c)
+            outs.append(o[:, :k].clone())
+        o, k = s.flush(chunks[0])
+        outs.append(o[:, :k].clone())
+        s.close()
+        return torch.cat(outs, dim=1)
+    y = run()
+    sg.set_exact(True)
+    ye = run()
+    sg.set_exact(False)
+    assert y.shape == (C_, 3 * K)             # total outputs == total inputs, fixed latency n
+    assert float((y - ye).abs().max()) <= 1e-6 * max(float(c.abs().max()) for c in chunks)
+    # the stream equals the batch filter (polynomial edges) on the concatenated signal
+    whole = torch.cat([c[:4096] for c in chunks], dim=1)
+    yb = sg.SavgolFilter(n, 2, 1, 1.0, "polynomial").apply(whole)
+    assert float((y[:4096] - yb).abs().max()) <= 1e-6 * float(whole.abs().max())
