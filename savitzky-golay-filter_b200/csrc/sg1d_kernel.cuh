@@ -154,11 +154,24 @@ __device__ __forceinline__ void stage_segment(float4* dst0 /* buf + lane + (lane
     const char* src0 = xrow + (o0 - PAD) * a.in_stride;        // only dereferenced inside [c_lo, c_hi)
     const bool vec_ok = rows_aligned || ((a.in_stride == 4) && ((reinterpret_cast<uintptr_t>(src0) & 15) == 0));
     if (vec_ok) {
+        // this lane's first chunk; the pointer is made opaque so that it stays in a register pair and
+        // every copy is "base + immediate" (otherwise it is re-derived from the kernel parameters
+        // with three extra instructions per copy)
         const char* s = src0 + lane * 16;
+        asm volatile("" : "+l"(s));
+        if (c_hi >= 256) {
+            // full segment: only the first pass (left pad chunks of a row's first segment) and the
+            // tail pass are conditional
+            if (lane >= c_lo) cp_async16(dst0, s);
 #pragma unroll
-        for (int it = 0; it < 9; ++it) {
-            const int c = lane + 32 * it;  // chunk c lives at c + (c >> 3) = dst0 + 36*it
-            if (c >= c_lo && c < c_hi) cp_async16(dst0 + 36 * it, s + 512 * it);
+            for (int it = 1; it < 8; ++it) cp_async16(dst0 + 36 * it, s + 512 * it);  // chunk lane + 32 it lives at dst0 + 36 it
+            if (lane + 256 < c_hi) cp_async16(dst0 + 36 * 8, s + 512 * 8);
+        } else {
+#pragma unroll
+            for (int it = 0; it < 9; ++it) {
+                const int c = lane + 32 * it;
+                if (c >= c_lo && c < c_hi) cp_async16(dst0 + 36 * it, s + 512 * it);
+            }
         }
     } else if (a.in_stride == 4) {
         constexpr int NE = (4 * ((kSeg + 2 * N + DELTA + 3) / 4) + 31) / 32;
