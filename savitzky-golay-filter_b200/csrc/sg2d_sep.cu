@@ -104,14 +104,32 @@ __device__ __noinline__ void emit_ragged(float* dst_row, const float2 (&v)[RX / 
         if (X + j >= Xlo && X + j < Xhi) dst_row[j] = (j & 1) ? v[j / 2].y : v[j / 2].x;
 }
 
+__device__ __forceinline__ void cp_async4_s(unsigned smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+
 __device__ __forceinline__ void cp_async16_s(unsigned smem_dst, const void* gsrc)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 
-__device__ __forceinline__ void cp_async4_s(unsigned smem_dst, const void* gsrc)
+
+// Pad columns of an edge strip, two rows: pad element q of the slot (the nl columns left of the image,
+// then those right of it) is copied from the column the boundary rule maps it to.  d = shared address of
+// the slot's first float (row t), r0 / r1 = start of the two source rows.  Out of line to keep the main
+// loop inside the instruction cache.
+__device__ __noinline__ void stage_pads(unsigned d, const float* r0, const float* r1, int row_bytes, int npad, int nl, int xb, int cols,
+                                        int boundary, int lane)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
+#pragma unroll 1
+    for (int q = lane; q < npad; q += 32) {
+        const int x = q < nl ? xb + q : cols + (q - nl);
+        const int m = map_index(x, cols, boundary);
+        const unsigned dd = d + 4 * (x - xb);
+        cp_async4_s(dd, r0 + m);
+        cp_async4_s(dd + row_bytes, r1 + m);
+    }
 }
 
 // Two rows of an EDGE STRIP (first / last strip of the image), or of an image whose rows are not 16-byte
@@ -164,8 +182,9 @@ __global__ void __launch_bounds__(kWarps * 32, RX >= 4 ? ((N <= 6 || (N == 7 && 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float(*ring)[ROWF] = s_ring[warp];
 
-    // 16-byte copies need aligned rows; other images take the per-chunk path for every strip
-    const bool rows_aligned = ((reinterpret_cast<uintptr_t>(a.in) & 15) | (a.in_stride & 3) | (a.in_image_pitch & 3)) == 0;
+    // 16-byte copies need aligned rows, whole chunks a width that is a multiple of 4; other images take the
+    // out-of-line per-chunk path for every strip
+    const bool simple_rows = ((reinterpret_cast<uintptr_t>(a.in) & 15) | (a.in_stride & 3) | (a.in_image_pitch & 3) | (a.cols & 3)) == 0;
     const int Ylo = a.cy, Yhi = a.cy + a.out_rows;      // stored region in full-image coordinates
     const int Xlo = a.cx, Xhi = a.cx + a.out_cols;
     const int strips = (Xhi + TW - 1) / TW;
@@ -181,7 +200,8 @@ __global__ void __launch_bounds__(kWarps * 32, RX >= 4 ? ((N <= 6 || (N == 7 && 
         if (lane == 0) ticket = atomicAdd(a.counter, 1u);
         const long long item = __shfl_sync(0xffffffffu, ticket, 0);
         if (item >= items) break;
-        // longest first: the items of the two edge strips (out-of-line staging, several times slower)
+        // longest first: the items of the two edge strips (extra pad-column copies; much slower on the
+        // out-of-line path of unaligned / ragged images)
         // are handed out before everything else, so none of them is left for the tail of the launch;
         // the interior strips follow image by image, band by band, neighbours in x back to back (their
         // halo columns meet in L2)
@@ -211,25 +231,35 @@ __global__ void __launch_bounds__(kWarps * 32, RX >= 4 ? ((N <= 6 || (N == 7 && 
         float* vout = a.out + img * a.out_image_pitch - static_cast<long long>(a.cy) * a.out_stride - a.cx;
 
         // ---- staging of input rows ----
-        // Strips that need no boundary rule in x (all but the first / last one) stage a row with one or
-        // two unconditional 16-byte copies per lane; interior bands advance a running source pointer,
-        // the first / last band maps the row index (clamp / reflect).  Edge strips go through the
-        // generic per-chunk path.
+        // Rows t, t+1 (t even) go to ring slots t mod 8 and the next one.  Images with 16-byte aligned
+        // rows and a width that is a multiple of 4 (chunks are then entirely inside or outside the image):
+        //   * chunks inside the image: one or two 16-byte copies per lane and row, predicate fixed per item
+        //     (always true for interior strips); interior bands advance a running source pointer, the
+        //     first / last band maps the row index (clamp / reflect);
+        //   * pad columns of the first / last strip: one element per lane (4-byte copy from the column
+        //     the boundary rule maps it to) -- 2 x 8 elements per step for a 15x15 window.
+        // Everything else (unaligned rows, ragged widths) takes the out-of-line per-chunk path.
         const int steps2 = (steps + 1) & ~1;   // rows are consumed two per step, see below
         const bool y_in = (Y0 - N >= 0) && (Y0 - N + steps2 <= a.rows);
-        const bool x_in = (x0 - PADX >= 0) && (x0 + TW + PADX <= a.cols) && rows_aligned;
+        const int xb = x0 - PADX;                                        // image column of the slot's first float
+        const int nl = xb < 0 ? -xb : 0;                                 // pad elements left of the image
+        const int nr = xb + ROWF > a.cols ? xb + ROWF - a.cols : 0;      // ... and right of it
+        const int npad = nl + nr;
+        const bool x_in = npad == 0;                                     // interior strip
+        bool pch[(ROWCH + 31) / 32];                                     // this lane's chunk(s) lie inside the image
+#pragma unroll
+        for (int c0 = 0; c0 < ROWCH; c0 += 32) {
+            const int xin = xb + 4 * (c0 + lane);
+            pch[c0 / 32] = (c0 + 32 <= ROWCH || lane < ROWCH - c0) && xin >= 0 && xin + 4 <= a.cols;
+        }
         float* const ring_lane = &ring[0][0] + 4 * lane;
         const unsigned ring_lane_s = static_cast<unsigned>(__cvta_generic_to_shared(ring_lane));
-        // this lane's first chunk of the NEXT row to stage (interior items)
-        const float* src_next = in + static_cast<long long>(Y0 - N) * a.in_stride + (x0 - PADX) + 4 * lane;
-        const float* const xbase = in + (x0 - PADX) + 4 * lane;
-        // Rows t, t+1 (t even) go to ring slots t mod 8 and the next one.  Strips that need no boundary
-        // rule in x (all but the first / last): two or three unconditional 16-byte copies per row from a
-        // running source pointer (interior bands) or from the rows the boundary rule designates (first /
-        // last band).  Edge strips take the out-of-line per-chunk path.
+        // this lane's first chunk of the NEXT row to stage (interior bands)
+        const float* src_next = in + static_cast<long long>(Y0 - N) * a.in_stride + xb + 4 * lane;
+        const float* const xbase = in + xb + 4 * lane;
         auto stage_pair = [&](int t) {
             const int slot = t & (kRing - 1);
-            if (x_in) {
+            if (simple_rows) {
                 const float *s0, *s1;
                 if (y_in) {
                     s0 = src_next;
@@ -240,17 +270,27 @@ __global__ void __launch_bounds__(kWarps * 32, RX >= 4 ? ((N <= 6 || (N == 7 && 
                     s1 = xbase + static_cast<long long>(map_index(Y0 - N + t + 1, a.rows, a.boundary)) * a.in_stride;
                 }
                 const unsigned d = ring_lane_s + slot * (ROWF * 4);
+                if (x_in) {   // interior strip: nothing to decide per lane
 #pragma unroll
-                for (int c0 = 0; c0 < ROWCH; c0 += 32)
-                    if (c0 + 32 <= ROWCH || lane < ROWCH - c0) {
-                        cp_async16_s(d + 16 * c0, s0 + 4 * c0);
-                        cp_async16_s(d + ROWF * 4 + 16 * c0, s1 + 4 * c0);
-                    }
+                    for (int c0 = 0; c0 < ROWCH; c0 += 32)
+                        if (c0 + 32 <= ROWCH || lane < ROWCH - c0) {
+                            cp_async16_s(d + 16 * c0, s0 + 4 * c0);
+                            cp_async16_s(d + ROWF * 4 + 16 * c0, s1 + 4 * c0);
+                        }
+                } else {
+#pragma unroll
+                    for (int c0 = 0; c0 < ROWCH; c0 += 32)
+                        if (pch[c0 / 32]) {
+                            cp_async16_s(d + 16 * c0, s0 + 4 * c0);
+                            cp_async16_s(d + ROWF * 4 + 16 * c0, s1 + 4 * c0);
+                        }
+                    stage_pads(d - 16 * lane, s0 - xb - 4 * lane, s1 - xb - 4 * lane, ROWF * 4, npad, nl, xb, a.cols, a.boundary, lane);
+                }
             } else {
                 stage_edge_pair<ROWCH, ROWF>(ring_lane_s + slot * (ROWF * 4),
                                              in + static_cast<long long>(map_index(Y0 - N + t, a.rows, a.boundary)) * a.in_stride,
                                              in + static_cast<long long>(map_index(Y0 - N + t + 1, a.rows, a.boundary)) * a.in_stride,
-                                             x0 - PADX, a.cols, a.boundary, lane);
+                                             xb, a.cols, a.boundary, lane);
             }
         };
         // store side, hoisted: this lane's columns, whether they lie inside the stored region and
@@ -347,6 +387,7 @@ __global__ void __launch_bounds__(kWarps * 32, RX >= 4 ? ((N <= 6 || (N == 7 && 
                 row_pass(t, h0);
                 row_pass(t + 1, h1);
 
+                float2 v0[RX / 2], v1[RX / 2];
                 static_switch<NA / 2>(phase, [&](auto sc) {
                     constexpr int s2 = 2 * decltype(sc)::value;   // ring position of row t
                     // column pass: row t is window row wy of output row t - wy -> slot (s2 - wy) mod NA, row
@@ -370,21 +411,17 @@ __global__ void __launch_bounds__(kWarps * 32, RX >= 4 ? ((N <= 6 || (N == 7 && 
                                 }
                             }
                         }
-                    // output rows t - 2n and t + 1 - 2n are complete
-                    if (t >= 2 * N && t - 2 * N < nrows) {
-                        float2 v[RX / 2];
+                    // output rows t - 2n and t + 1 - 2n are complete (their slots are dead until wy = 0 re-opens
+                    // them, so these copies fold into the last FFMA2 of each row)
 #pragma unroll
-                        for (int jp = 0; jp < RX / 2; ++jp) v[jp] = acc[jp][(s2 + 2) % NA];
-                        emit(v);
-                    }
-                    if (t + 1 >= 2 * N && t + 1 - 2 * N < nrows) {
-                        float2 v[RX / 2];
-#pragma unroll
-                        for (int jp = 0; jp < RX / 2; ++jp) v[jp] = acc[jp][(s2 + 3) % NA];
-                        emit(v);
+                    for (int jp = 0; jp < RX / 2; ++jp) {
+                        v0[jp] = acc[jp][(s2 + 2) % NA];
+                        v1[jp] = acc[jp][(s2 + 3) % NA];
                     }
                 });
                 phase = phase + 1 == NA / 2 ? 0 : phase + 1;
+                if (t >= 2 * N && t - 2 * N < nrows) emit(v0);
+                if (t + 1 >= 2 * N && t + 1 - 2 * N < nrows) emit(v1);
             }
         } else {
 #pragma unroll 1
