@@ -5,19 +5,22 @@
 // the order-2/3 smoothing filters), all row factors even or all odd in x.
 //
 // Execution plan -- warp-autonomous, like the 1D kernel; no __syncthreads anywhere:
-//   * work item = (image, band of 512 output rows, strip of 32*RX output columns); a warp walks DOWN
-//     its strip one input row per step.  Rows are staged by cp.async into a private ring of 8 row
-//     buffers, 6 rows ahead of the row being consumed (~3.4 KB in flight per warp); the row index is
-//     mapped by the boundary rule (clamp / half-sample reflect), the few pad columns of the first /
-//     last strip go through a per-element edge path, so the compute is boundary agnostic.
+//   * work item = (image, band of <= 512 output rows, strip of 32*RX output columns), handed out by an
+//     atomic ticket (edge strips first); a warp walks DOWN its strip two input rows per step.  Rows are
+//     staged by cp.async into a private ring of 8 row buffers, 6 rows ahead of the rows being consumed
+//     (~3.4 KB in flight per warp); the row index is mapped by the boundary rule (clamp / half-sample
+//     reflect), the few pad columns of the first / last strip are copied element by element from the
+//     column the rule maps them to, so the compute is boundary agnostic.
 //   * ROW PASS: each lane owns RX consecutive columns; from a register window of the staged row it
 //     forms the folded sums s_k = x[c+k] +/- x[c-k] once and evaluates the R row factors on them
 //     (n adds + R*(n+1) FMAs per pixel instead of R*(2n+1) MACs; the FMAs packed over column pairs).
-//   * COLUMN PASS, in registers: the lane keeps the 2n+1 partially accumulated output rows of its
-//     columns.  The R values just produced are scattered into them with packed FFMA2 (column pairs
-//     packed, weight col[wy] broadcast from a uniform register), the oldest row is complete and is
-//     stored (one 512-byte store per warp and row).  Accumulator indices are static inside blocks
-//     of U = 4 rows; a block ends with a register shift.
+//   * COLUMN PASS, in registers: the lane keeps the partially accumulated output rows of its columns.
+//     The R values just produced are scattered into them with packed FFMA2 (column pairs packed,
+//     weight col[wy] broadcast from a uniform register), the two oldest rows are complete and are
+//     stored (one 512-byte store per warp and row).  Half-windows <= 8: a static ring of 2n+2 rows
+//     whose indices are compile-time constants per ring phase (one copy of the column pass per
+//     phase, selected by a switch; no register ever moves).  Larger half-windows: indices static
+//     inside blocks of U = 4 rows, a block ends with a register shift.
 //   => every input pixel is read from HBM once and from shared memory (RX+2n)/RX times, no
 //      intermediate image ever exists, and there is no vertical halo recomputation except the 2n
 //      warm-up rows per band.
@@ -38,6 +41,9 @@ namespace sg { extern std::atomic<unsigned long long> g_launches; }
 #endif
 #ifndef SG2D_RX4
 #define SG2D_RX4 1
+#endif
+#ifndef SG2D_WIDE_MINB
+#define SG2D_WIDE_MINB 2   // resident CTAs for the widest rank-3/4 kernels (231 registers unconstrained)
 #endif
 #ifndef SG2D_RING
 #define SG2D_RING 1
@@ -163,7 +169,7 @@ __device__ __noinline__ void stage_edge_pair(unsigned d, const float* r0, const 
 }
 
 template <int N, int R, int RX>
-__global__ void __launch_bounds__(kWarps * 32, RX >= 4 ? ((N <= 6 || (N == 7 && (R == 2 || R == 3))) ? SG2D_MINB : 3) : SG2D_MINB2) sep_kernel(const __grid_constant__ SepW<R> w,
+__global__ void __launch_bounds__(kWarps * 32, RX >= 4 ? ((N <= 6 || (N == 7 && (R == 2 || R == 3))) ? SG2D_MINB : 3) : ((N >= 15 && R >= 3) ? SG2D_WIDE_MINB : SG2D_MINB2)) sep_kernel(const __grid_constant__ SepW<R> w,
                                                                             const __grid_constant__ Args2D a)
 {
     constexpr int TW = 32 * RX;                 // output columns per strip
@@ -171,7 +177,10 @@ __global__ void __launch_bounds__(kWarps * 32, RX >= 4 ? ((N <= 6 || (N == 7 && 
     constexpr int DX = PADX - N;
     constexpr int ROWF = TW + 2 * PADX;         // floats per staged row
     constexpr int ROWCH = ROWF / 4;             // 16-byte chunks per staged row
-    constexpr bool RING = SG2D_RING && N <= 8;  // static accumulator ring (main loop unrolled n+1 steps) vs shifting blocks
+    // static accumulator ring (one column pass per ring phase) vs shifting blocks: the ring needs
+    // (n+1) copies of the column pass, which must stay inside the 32 KB instruction cache
+    // (17x17 rank-4: 2448 FFMA2, measured 9 % slower than the shifting blocks)
+    constexpr bool RING = SG2D_RING && N <= 8 && (N + 1) * (2 * N + 1) * R * RX <= 1500;
     constexpr int NA = RING ? 2 * N + 2 : 2 * N + kU;   // output rows in flight per column
     constexpr int WIN = RX + DX + 2 * N;        // floats of the row window a lane touches
     constexpr int VW = RX >= 4 ? 4 : 2;         // floats per shared load
@@ -242,10 +251,7 @@ __global__ void __launch_bounds__(kWarps * 32, RX >= 4 ? ((N <= 6 || (N == 7 && 
         const int steps2 = (steps + 1) & ~1;   // rows are consumed two per step, see below
         const bool y_in = (Y0 - N >= 0) && (Y0 - N + steps2 <= a.rows);
         const int xb = x0 - PADX;                                        // image column of the slot's first float
-        const int nl = xb < 0 ? -xb : 0;                                 // pad elements left of the image
-        const int nr = xb + ROWF > a.cols ? xb + ROWF - a.cols : 0;      // ... and right of it
-        const int npad = nl + nr;
-        const bool x_in = npad == 0;                                     // interior strip
+        const bool x_in = xb >= 0 && xb + ROWF <= a.cols;                // interior strip: no pad columns
         bool pch[(ROWCH + 31) / 32];                                     // this lane's chunk(s) lie inside the image
 #pragma unroll
         for (int c0 = 0; c0 < ROWCH; c0 += 32) {
@@ -284,7 +290,9 @@ __global__ void __launch_bounds__(kWarps * 32, RX >= 4 ? ((N <= 6 || (N == 7 && 
                             cp_async16_s(d + 16 * c0, s0 + 4 * c0);
                             cp_async16_s(d + ROWF * 4 + 16 * c0, s1 + 4 * c0);
                         }
-                    stage_pads(d - 16 * lane, s0 - xb - 4 * lane, s1 - xb - 4 * lane, ROWF * 4, npad, nl, xb, a.cols, a.boundary, lane);
+                    const int nl = xb < 0 ? -xb : 0;                                 // pad elements left of the image
+                    const int nr = xb + ROWF > a.cols ? xb + ROWF - a.cols : 0;      // ... and right of it
+                    stage_pads(d - 16 * lane, s0 - xb - 4 * lane, s1 - xb - 4 * lane, ROWF * 4, nl + nr, nl, xb, a.cols, a.boundary, lane);
                 }
             } else {
                 stage_edge_pair<ROWCH, ROWF>(ring_lane_s + slot * (ROWF * 4),
