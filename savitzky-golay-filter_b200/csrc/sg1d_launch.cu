@@ -30,10 +30,12 @@ const Kernel1D* sg1d_group_table(int group)
 
 namespace {
 struct GridInfo { int blocks_per_sm = 0; };
-GridInfo g_grid[kMaxN + 1][V_COUNT][3];  // per (n, variant, packing); filled lazily (same value on every B200)
+GridInfo g_grid[kMaxN + 1][V_COUNT][5];  // per (n, variant, packing); filled lazily (same value on every B200)
 int g_sms[64];
 std::mutex g_mu;
 }  // namespace
+
+constexpr size_t kPackedSmemMax = 110 * 1024;  // two CTAs per SM
 
 // dynamic shared memory of the short-row kernel: 2 buffers per warp of 32/g row slots + edge values
 static size_t packed_smem_bytes(int n, bool lead2n, int g)
@@ -41,7 +43,7 @@ static size_t packed_smem_bytes(int n, bool lead2n, int g)
     const int lead = lead2n ? 2 * n : n;
     const int delta = ((lead + 3) & ~3) - lead;
     const int rpg = 32 / g, warps = kThreads / 32;
-    return static_cast<size_t>(warps) * 2 * rpg * packed_slot_chunks(n, delta, g) * 16 + static_cast<size_t>(warps) * rpg * 2 * kMaxN * 4;
+    return static_cast<size_t>(warps) * 2 * rpg * packed_slot_chunks(n, delta, g) * 16 + static_cast<size_t>(warps) * rpg * 2 * n * 4;
 }
 
 cudaError_t sg1d_launch(int n, int variant, const W1D& w, Args1D& a, cudaStream_t stream)
@@ -52,9 +54,13 @@ cudaError_t sg1d_launch(int n, int variant, const W1D& w, Args1D& a, cudaStream_
     size_t smem = 0;
     a.pack_g = 0;
     if ((variant == V_BATCH_FAST || variant == V_STREAM_FAST) && a.len <= 512 && a.rows > 1) {
-        a.pack_g = a.len <= 128 ? 4 : a.len <= 256 ? 8 : 16;
-        gi_idx = a.pack_g == 4 ? 0 : a.pack_g == 8 ? 1 : 2;
-        smem = packed_smem_bytes(n, variant == V_STREAM_FAST, a.pack_g);
+        // lanes per row; wide windows on very short rows would need more shared memory per row slot than
+        // two resident CTAs allow: fewer, wider slots then
+        int g = a.len <= 32 ? 1 : a.len <= 64 ? 2 : a.len <= 128 ? 4 : a.len <= 256 ? 8 : 16;
+        while (g < 16 && packed_smem_bytes(n, variant == V_STREAM_FAST, g) > kPackedSmemMax) g *= 2;
+        a.pack_g = g;
+        gi_idx = g == 1 ? 0 : g == 2 ? 1 : g == 4 ? 2 : g == 8 ? 3 : 4;
+        smem = packed_smem_bytes(n, variant == V_STREAM_FAST, g);
         variant = variant == V_BATCH_FAST ? V_PACK_BATCH_FAST : V_PACK_STREAM_FAST;
     } else if (variant >= V_PACK_BATCH_FAST) {
         return cudaErrorInvalidValue;
@@ -68,11 +74,11 @@ cudaError_t sg1d_launch(int n, int variant, const W1D& w, Args1D& a, cudaStream_
     {
         std::lock_guard<std::mutex> lk(g_mu);
         GridInfo& gi = g_grid[n][variant][gi_idx];
+        if (smem > 48 * 1024) {   // per device and function; cheap enough to repeat
+            e = cudaFuncSetAttribute(k.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kPackedSmemMax));
+            if (e != cudaSuccess) return e;
+        }
         if (gi.blocks_per_sm == 0) {
-            if (smem > 48 * 1024) {
-                e = cudaFuncSetAttribute(k.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-                if (e != cudaSuccess) return e;
-            }
             int nb = 0;
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k.kernel, kThreads, smem);
             if (e != cudaSuccess) return e;

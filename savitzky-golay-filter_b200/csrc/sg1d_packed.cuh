@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(kThreads, N <= 18 ? 4 : 3) sg1d_packed_kernel(
     constexpr int kWarps = kThreads / 32;
 
     extern __shared__ __align__(16) float4 s_dyn[];
-    const int g = a.pack_g;                       // lanes per row: 16, 8 or 4
+    const int g = a.pack_g;                       // lanes per row: 16, 8, 4, 2 or 1
     const int rpg = 32 / g;                       // rows per warp group
     const int SLOT = packed_slot_chunks(N, DELTA, g);
     const int buf_chunks = rpg * SLOT;
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(kThreads, N <= 18 ? 4 : 3) sg1d_packed_kernel(
     const int slot = lane / g, p = lane - slot * g;
     float4* buf_cur = s_dyn + (warp * 2 + 0) * buf_chunks;
     float4* buf_nxt = s_dyn + (warp * 2 + 1) * buf_chunks;
-    float* s_edge = reinterpret_cast<float*>(s_dyn + kWarps * 2 * buf_chunks) + warp * (rpg * 2 * kMaxN);  // [slot][lead | trail]
+    float* s_edge = reinterpret_cast<float*>(s_dyn + kWarps * 2 * buf_chunks) + warp * (rpg * 2 * N);  // [slot][lead n | trail n]
 
     const long long len = a.len;
     const int ilen = static_cast<int>(len);
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(kThreads, N <= 18 ? 4 : 3) sg1d_packed_kernel(
         cp_async_commit();
 
         // polynomial edges of this slot's row: its g lanes share the 2n edge outputs
-        float* se = s_edge + slot * (2 * kMaxN);
+        float* se = s_edge + slot * (2 * N);
         if (active && (a.edge_lead || a.edge_trail)) {
             for (int e = p; e < N; e += g) {
                 if (a.edge_lead) {
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(kThreads, N <= 18 ? 4 : 3) sg1d_packed_kernel(
                     const long long base = len - WS;
                     const float s = dot_ordered<WS, ARITH_FAST>([&](int k) { return a.edge_t[k * 32 + e]; },
                                                                 [&](int k) { return ld_sample(xrow, a.in_stride, base + k); });
-                    se[kMaxN + e] = s * a.scale;
+                    se[N + e] = s * a.scale;
                 }
             }
         }
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kThreads, N <= 18 ? 4 : 3) sg1d_packed_kernel(
             for (int j = 0; j < kR; ++j) {
                 const int oj = o + j;
                 if (a.edge_lead && oj < N) out[j] = se[oj];
-                else if (a.edge_trail && oj >= ilen - N && oj < ilen) out[j] = se[kMaxN + (ilen - 1 - oj)];
+                else if (a.edge_trail && oj >= ilen - N && oj < ilen) out[j] = se[N + (ilen - 1 - oj)];
             }
         }
 
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kThreads, N <= 18 ? 4 : 3) sg1d_packed_kernel(
         {
             const int lim = static_cast<int>(a.out_len < len ? a.out_len : len);
             const long long row0 = static_cast<long long>(grp) * rpg;
-            const int shift = g == 16 ? 9 : g == 8 ? 8 : 7;  // log2(outputs parked per slot)
+            const int shift = 36 - __clz(g);                  // log2(outputs parked per slot) = 5 + log2(g)
             if (out_aligned) {
                 // chunk q = lane + 32 i of the group's parked outputs: 512 contiguous bytes per store
 #pragma unroll

@@ -244,11 +244,11 @@ def test_signal_longer_than_2_31_samples_periodic(oracle):
 
 @pytest.mark.parametrize("n,m,d,dt", [(1, 1, 0, 1.0), (4, 2, 1, 0.5), (12, 4, 0, 1.0), (16, 3, 1, 1.0), (25, 4, 2, 1.0), (32, 5, 0, 1.0)])
 def test_short_row_batches_share_warps(oracle, n, m, d, dt):
-    # rows of <= 512 samples run in the packed kernel (2, 4 or 8 signals per warp, sg1d_packed.cuh):
+    # rows of <= 512 samples run in the packed kernel (2 ... 32 signals per warp, sg1d_packed.cuh):
     # every packing width, ragged row counts, aligned / odd pitches, offset views
     rng = np.random.default_rng(77 + n)
     ws = 2 * n + 1
-    lengths = sorted({ws, ws + 1, 100 + n, 128, 129, 200, 256, 257, 360, 511, 512})
+    lengths = sorted({ws, ws + 1, max(ws, 31), max(ws, 32), max(ws, 33), max(ws, 64), 65 + n, 100 + n, 128, 129, 200, 256, 257, 360, 511, 512})
     for L in lengths:
         for rows in (2, 3, 9, 64, 333):
             pitch = L + (0 if rows % 2 == 0 else 3)

@@ -20,7 +20,7 @@ for n, m, d in [(1, 1, 0), (7, 3, 1), (16, 3, 1), (21, 4, 2), (32, 4, 2)]:
 for n, m, d in [(2, 2, 0), (12, 4, 0), (25, 4, 2), (32, 5, 0)]:
     for mode in ("polynomial", "reflect", "periodic", "constant"):
         f = sg.SavgolFilter(n, m, d, 1.0, mode)
-        for rows, L, pitch in [(7, 2 * n + 1, 2 * n + 1), (33, 128, 128), (9, 250, 253), (5, 360, 360), (17, 512, 516), (3, 100, 101)]:
+        for rows, L, pitch in [(7, 2 * n + 1, 2 * n + 1), (40, 20, 20), (70, 50, 51), (33, 64, 64), (33, 128, 128), (9, 250, 253), (5, 360, 360), (17, 512, 516), (3, 100, 101)]:
             if L < 2 * n + 1:
                 continue
             big = torch.from_numpy(rng.standard_normal((rows, pitch + 1)).astype(np.float32)).cuda()
