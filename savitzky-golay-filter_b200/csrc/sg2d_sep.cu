@@ -45,6 +45,9 @@ namespace sg { extern std::atomic<unsigned long long> g_launches; }
 #ifndef SG2D_WIDE_MINB
 #define SG2D_WIDE_MINB 2   // resident CTAs for the widest rank-3/4 kernels (231 registers unconstrained)
 #endif
+#ifndef SG2D_RING_MAX
+#define SG2D_RING_MAX 1500   // FFMA2 in all column-pass copies of the static ring
+#endif
 #ifndef SG2D_RING
 #define SG2D_RING 1
 #endif
@@ -180,7 +183,8 @@ __global__ void __launch_bounds__(kWarps * 32, RX >= 4 ? ((N <= 6 || (N == 7 && 
     // static accumulator ring (one column pass per ring phase) vs shifting blocks: the ring needs
     // (n+1) copies of the column pass, which must stay inside the 32 KB instruction cache
     // (17x17 rank-4: 2448 FFMA2, measured 9 % slower than the shifting blocks)
-    constexpr bool RING = SG2D_RING && N <= 8 && (N + 1) * (2 * N + 1) * R * RX <= 1500;
+    // (2 columns per lane, half-windows 9-16: the ring measured 9 % slower than the blocks at 25x25)
+    constexpr bool RING = SG2D_RING && N <= 8 && (N + 1) * (2 * N + 1) * R * RX <= SG2D_RING_MAX;
     constexpr int NA = RING ? 2 * N + 2 : 2 * N + kU;   // output rows in flight per column
     constexpr int WIN = RX + DX + 2 * N;        // floats of the row window a lane touches
     constexpr int VW = RX >= 4 ? 4 : 2;         // floats per shared load
