@@ -32,3 +32,14 @@ def test_reference_demo_program_runs():
     p = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0
     assert re.search(r"Verification: PASS \(0 mismatches\)", p.stdout), p.stdout[-1500:]
+
+
+def test_extension_api_from_plain_c():
+    # examples/c_extensions.c: batch / multichannel stream / checkpoint / 2D batch called from C99 with host
+    # buffers, each checked against the reference-shaped single-call API of the same library
+    exe = os.path.join(BIN, "c_extensions_b200")
+    if not os.path.exists(exe):
+        pytest.skip("drop-in binaries not built")
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-1500:] + p.stderr[-1500:]
+    assert p.stdout.count("[PASS]") == 4 and "[FAIL]" not in p.stdout, p.stdout
