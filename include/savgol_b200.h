@@ -283,6 +283,18 @@ int savgol2d_apply_batch(const Savgol2DFilter *filter,
                          float *output, int out_stride, size_t out_image_pitch,
                          size_t n_images, Savgol2DBoundary boundary);
 
+/* One horizontal band of a larger image (row-band sharding of a single huge image over several
+ * GPUs; device pointers).  `input` is a buffer of `rows` rows: `top_halo` rows that precede the
+ * band in the image, the band itself, `bottom_halo` rows that follow it.  A halo count is either
+ * half_window_y (the neighbour's rows, fetched by the caller) or 0, meaning that side of the band
+ * is the image border and follows `boundary` (CONSTANT or REFLECT).  The rows - top_halo -
+ * bottom_halo filtered band rows go to `output` (row 0 = first band row); they are bit-identical
+ * to the same rows of savgol2d_apply() on the whole image.  Returns 0 / -1. */
+int savgol2d_apply_band(const Savgol2DFilter *filter,
+                        const float *input, int rows, int cols, int in_stride,
+                        float *output, int out_stride, Savgol2DBoundary boundary,
+                        int top_halo, int bottom_halo);
+
 /* Multi-channel chunked stream ------------------------------------------- */
 
 /* `channels` independent streams advanced in lockstep, one chunk of K samples per

@@ -376,6 +376,20 @@ class Savgol2DFilter:
             raise RuntimeError("savgol2d_apply_valid failed")
         return out
 
+    def apply_band(self, buf, top_halo, bottom_halo, boundary="constant", out=None):
+        """One horizontal band of a larger image: ``buf`` = [top_halo rows | band | bottom_halo rows] (device
+        tensor); a halo of 0 rows marks an image border.  Returns the filtered band rows."""
+        xp, _k, _ = _prep(buf)
+        rows, cols = buf.shape
+        if out is None:
+            out = _empty_like(buf, (rows - top_halo - bottom_halo, cols))
+        op, _ko, _ = _prep(out, "output")
+        rc = lib().savgol2d_apply_band(self._h, xp, rows, cols, _row_pitch(buf), op, _row_pitch(out), BOUNDARY_2D[boundary],
+                                       int(top_halo), int(bottom_halo))
+        if rc != 0:
+            raise RuntimeError("savgol2d_apply_band failed (see stderr)")
+        return out
+
     def close(self):
         if getattr(self, "_h", None):
             lib().savgol2d_destroy(self._h)

@@ -63,7 +63,8 @@ const float* weights_device(const Savgol2DFilter* f, cudaStream_t st, float** te
 
 // One launch over device-resident images.
 bool run2d_device(const Savgol2DFilter* f, const float* in, int rows, int cols, long long is, long long ipitch,
-                  float* out, long long os, long long opitch, long long n_images, int boundary, cudaStream_t st)
+                  float* out, long long os, long long opitch, long long n_images, int boundary, cudaStream_t st,
+                  int top_halo = -1, int bottom_halo = -1)
 {
     const int nx = f->config.half_window_x, ny = f->config.half_window_y;
     sg2d::Args2D a{};
@@ -75,7 +76,12 @@ bool run2d_device(const Savgol2DFilter* f, const float* in, int rows, int cols, 
     a.n_images = n_images;
     a.boundary = boundary;
     a.scale = f->scale;
-    if (boundary == sg2d::B_VALID) {
+    if (top_halo >= 0) {
+        // band of a larger image: the buffer holds halo rows above / below, only the rows in between are
+        // produced; a side without halo is a true image border and follows the boundary rule
+        a.out_rows = rows - top_halo - bottom_halo; a.out_cols = cols;
+        a.cy = top_halo; a.cx = 0;
+    } else if (boundary == sg2d::B_VALID) {
         a.out_rows = rows - 2 * ny; a.out_cols = cols - 2 * nx;
         a.cy = ny; a.cx = nx;
     } else {
@@ -222,6 +228,35 @@ void savgol2d_destroy(Savgol2DFilter* filter)
     }
     free(filter->weights);
     free(filter);
+}
+
+int savgol2d_apply_band(const Savgol2DFilter* filter, const float* input, int rows, int cols, int in_stride, float* output,
+                        int out_stride, Savgol2DBoundary boundary, int top_halo, int bottom_halo)
+{
+    if (!filter || !input || !output) return -1;
+    const int ny = filter->config.half_window_y;
+    if (boundary != SAVGOL2D_BOUNDARY_CONSTANT && boundary != SAVGOL2D_BOUNDARY_REFLECT) {
+        fprintf(stderr, "savgol2d_apply_band: boundary must be CONSTANT or REFLECT\n");
+        return -1;
+    }
+    if ((top_halo != 0 && top_halo != ny) || (bottom_halo != 0 && bottom_halo != ny) || cols <= 0 ||
+        rows - top_halo - bottom_halo <= 0) {
+        fprintf(stderr, "savgol2d_apply_band: halos must be 0 (image border) or half_window_y rows, band must not be empty\n");
+        return -1;
+    }
+    if (!sge::device_ready(true)) return -1;
+    if (sge::classify(input) != MemKind::Device || sge::classify(output) != MemKind::Device) {
+        fprintf(stderr, "savgol2d_apply_band: band and output must be device pointers\n");
+        return -1;
+    }
+    const size_t in_span = static_cast<size_t>(rows - 1) * in_stride + cols;
+    const size_t out_span = static_cast<size_t>(rows - top_halo - bottom_halo - 1) * out_stride + cols;
+    if (ranges_overlap2d(input, in_span, output, out_span)) {
+        fprintf(stderr, "savgol2d_apply_band: output must not overlap the band buffer\n");
+        return -1;
+    }
+    return run2d_device(filter, input, rows, cols, in_stride, 0, output, out_stride, 0, 1, static_cast<int>(boundary),
+                        sge::current_stream(), top_halo, bottom_halo) ? 0 : -1;
 }
 
 int savgol2d_apply_batch(const Savgol2DFilter* filter, const float* input, int rows, int cols, int in_stride,

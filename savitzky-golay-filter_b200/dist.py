@@ -121,3 +121,36 @@ class PeerRing:
         for p, o in self._mapped:
             self._lib.savgol_b200_ipc_close(C.c_void_p(p), C.c_size_t(o))
         self._mapped = []
+
+
+def exchange_halo_rows(band, ny: int, group=None):
+    """Row-band sharding of one image: returns (top, bottom) = the ny image rows above / below this rank's
+    band (bands in rank order), or None at the image border.  One all_gather of a [2*ny, cols] strip."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if band.shape[0] < ny:
+        raise ValueError("every band must hold at least half_window_y rows")
+    if world == 1:
+        return None, None
+    strip = torch.cat([band[:ny], band[-ny:]]).contiguous()
+    flat = torch.empty(world * strip.numel(), dtype=band.dtype, device=band.device)
+    dist.all_gather_into_tensor(flat, strip.reshape(-1), group=group)
+    gathered = flat.view((world,) + tuple(strip.shape))
+    top = gathered[rank - 1, ny:] if rank > 0 else None
+    bottom = gathered[rank + 1, :ny] if rank < world - 1 else None
+    return top, bottom
+
+
+def apply_image_bands(filt, band, boundary="constant", out=None, group=None):
+    """Filters this rank's horizontal band of ONE image sharded by rows over the group: halo rows from the
+    ring neighbours, then savgol2d_apply_band.  The result equals the same rows of the whole-image filter."""
+    import torch
+
+    ny = int(filt.config.half_window_y)
+    top, bottom = exchange_halo_rows(band, ny, group)
+    parts = ([top] if top is not None else []) + [band] + ([bottom] if bottom is not None else [])
+    buf = torch.cat(parts).contiguous() if len(parts) > 1 else band
+    return filt.apply_band(buf, ny if top is not None else 0, ny if bottom is not None else 0, boundary, out=out)

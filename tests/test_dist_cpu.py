@@ -82,3 +82,53 @@ def test_partitioned_signal_halo_exchange_gloo(world, mode):
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) == 1
+
+
+class _OracleBandFilter:
+    """Stand-in for Savgol2DFilter.apply_band on CPU: the oracle over [halo | band | halo], cropped -- the
+    contract tests/test_gpu_2d.py checks for savgol2d_apply_band on the device."""
+
+    def __init__(self, O, nx, ny, order):
+        self.o = O.Filter2D(nx, ny, order)
+
+        class _Cfg:
+            half_window_y = ny
+        self.config = _Cfg()
+
+    def apply_band(self, buf, top, bottom, boundary, out=None):
+        full = self.o.apply(buf.numpy().copy(), boundary)
+        return torch.from_numpy(full[top: full.shape[0] - bottom].copy())
+
+
+def _band_worker(rank, world, port, boundary, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from savgol_b200 import dist as sgd
+    from oracle import oracle as O
+    nx, ny, order = 3, 4, 3
+    rng = np.random.default_rng(11)
+    img = rng.standard_normal((97, 40)).astype(np.float32)
+    a, b = sgd.shard_range(img.shape[0], rank, world)
+    f = _OracleBandFilter(O, nx, ny, order)
+    y = sgd.apply_image_bands(f, torch.from_numpy(img[a:b].copy()), boundary).numpy()
+    ref = O.Filter2D(nx, ny, order).apply(img, boundary)[a:b]
+    ok = y.shape == ref.shape and np.array_equal(y.view(np.uint32), ref.view(np.uint32))
+    t = torch.tensor([1 if ok else 0])
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        q.put(int(t.item()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,boundary", [(2, "constant"), (3, "reflect")])
+def test_image_row_bands_halo_exchange_gloo(world, boundary):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_band_worker, args=(r, world, port, boundary, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+    assert all(p.exitcode == 0 for p in procs)
+    assert q.get(timeout=10) == 1

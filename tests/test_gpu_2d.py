@@ -180,3 +180,28 @@ def test_streaming_kernel_bands_strips_and_edges(oracle, n, ny, order, dx, dy):
                 o.apply(x[i], b, ref)
                 err = float(np.max(np.abs(got[i] - ref)))
                 assert err <= tol, (images, rows, cols, b, i, err, tol)
+
+
+@pytest.mark.parametrize("boundary", ["constant", "reflect"])
+def test_row_bands_reassemble_whole_image(oracle, boundary):
+    # savgol2d_apply_band: bands of one image (the per-GPU pieces of a row-sharded image) == whole-image rows, bit for bit
+    rng = np.random.default_rng(77)
+    img = torch.from_numpy(rng.standard_normal((700, 520)).astype(np.float32)).cuda()
+    for nx, ny, order in ((7, 7, 3), (3, 5, 4)):
+        f = sg.Savgol2DFilter(nx, ny, order)
+        for exact in (False, True):
+            sg.set_exact(exact)
+            whole = f.apply(img, boundary)
+            out = torch.empty_like(img)
+            cuts = [0, ny, 233, 240, 611, 700]
+            for lo, hi in zip(cuts[:-1], cuts[1:]):
+                top = ny if lo > 0 else 0
+                bottom = ny if hi < 700 else 0
+                f.apply_band(img[lo - top: hi + bottom], top, bottom, boundary, out=out[lo:hi])
+            sg.set_exact(False)
+            assert torch.equal(out, whole), (nx, ny, order, exact, boundary)
+        f.close()
+    lib = sg.lib()
+    f = sg.Savgol2DFilter(2, 2, 2)
+    assert lib.savgol2d_apply_band(f.handle, img.data_ptr(), 50, 520, 520, img.data_ptr() + 4 * 520 * 100, 520, 1, 1, 0) == -1   # halo != ny
+    assert lib.savgol2d_apply_band(f.handle, img.data_ptr(), 50, 520, 520, img.data_ptr() + 4 * 520 * 100, 520, 0, 2, 2) == -1   # VALID
