@@ -8,6 +8,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 
@@ -22,7 +23,8 @@ namespace {
 bool allocation_base(const void* p, char** base)
 {
     typedef CUresult (*GetRange)(CUdeviceptr*, size_t*, CUdeviceptr);
-    static GetRange fn = nullptr;
+    static std::atomic<GetRange> s_fn{nullptr};
+    GetRange fn = s_fn.load(std::memory_order_acquire);
     if (!fn) {
         void* f = nullptr;
         cudaDriverEntryPointQueryResult q;
@@ -30,6 +32,7 @@ bool allocation_base(const void* p, char** base)
             q != cudaDriverEntryPointSuccess)
             return false;
         fn = reinterpret_cast<GetRange>(f);
+        s_fn.store(fn, std::memory_order_release);
     }
     CUdeviceptr b = 0;
     size_t size = 0;

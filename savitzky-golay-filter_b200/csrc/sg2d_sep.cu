@@ -538,14 +538,18 @@ cudaError_t launch_nr(const Args2D& a, const SepPlan& plan, cudaStream_t stream)
     }
     w.sx = plan.parity_x < 0 ? -1.0f : 1.0f;
     auto kern = sep_kernel<N, R, RX>;
-    static int bps = 0, sms = 0;
-    if (bps == 0) {
+    // resident CTAs per SM / SM count of this instantiation (same on every B200; filled once, any thread)
+    static std::atomic<int> s_bps{0}, s_sms{0};
+    int bps = s_bps.load(std::memory_order_acquire), sms = s_sms.load(std::memory_order_acquire);
+    if (bps == 0 || sms == 0) {
         int dev = 0, nb = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kWarps * 32, 0);
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kWarps * 32, 0);
         if (e != cudaSuccess) return e;
         bps = nb > 0 ? nb : 1;
+        s_sms.store(sms, std::memory_order_release);
+        s_bps.store(bps, std::memory_order_release);
     }
     constexpr int TW = 32 * RX;
     const long long strips = (a.cx + a.out_cols + TW - 1) / TW;
