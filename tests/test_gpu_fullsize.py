@@ -74,6 +74,15 @@ def test_config4_full_images(oracle):
     ref = o.apply(crop, "constant")
     got = ye[3, :200 - 7, cols - 300 + 7:].cpu().numpy()
     assert np.array_equal(got.view(np.uint32), ref[:200 - 7, 7:].view(np.uint32))
+    # where the 7e-7 between the two flavours comes from: against a float64 evaluation of the same fp32 weight
+    # table the separable kernel is several times closer than the reference's 225-term sequential fp32 sum
+    from scipy.signal import correlate2d
+    c64 = x[3, 1000:1300, 2000:2400].cpu().numpy().astype(np.float64)
+    truth = correlate2d(c64, o.W.astype(np.float64), mode="valid") * np.float64(np.float32(o.scale))
+    fast = y[3, 1007:1293, 2007:2393].cpu().numpy().astype(np.float64)
+    exact = ye[3, 1007:1293, 2007:2393].cpu().numpy().astype(np.float64)
+    e_fast, e_ref = np.abs(fast - truth).max(), np.abs(exact - truth).max()
+    assert e_fast <= 3e-7 and e_fast <= e_ref, (e_fast, e_ref)
     # an order-3 filter reproduces cubic surfaces in the interior
     yy, xx = torch.meshgrid(torch.arange(512, device="cuda", dtype=torch.float32), torch.arange(512, device="cuda", dtype=torch.float32), indexing="ij")
     surf = 1e-6 * (xx ** 3) - 2e-4 * xx * yy + 0.01 * yy + 3.0
