@@ -283,6 +283,11 @@ int savgol2d_apply_batch(const Savgol2DFilter *filter,
                          float *output, int out_stride, size_t out_image_pitch,
                          size_t n_images, Savgol2DBoundary boundary);
 
+/* Diagnostics: the separable factorisation the fast 2D kernel uses for this filter.  *rank = number of
+ * (column factor x row factor) terms, 0 if the weight table was not accepted (every apply then runs the
+ * literal window kernel); *sum_err = sum |W - sum_r col_r x row_r| over the table.  Host only.  0 / -1. */
+int savgol2d_b200_plan(const Savgol2DFilter *filter, int *rank, float *sum_err);
+
 /* One horizontal band of a larger image (row-band sharding of a single huge image over several
  * GPUs; device pointers).  `input` is a buffer of `rows` rows: `top_halo` rows that precede the
  * band in the image, the band itself, `bottom_halo` rows that follow it.  A halo count is either

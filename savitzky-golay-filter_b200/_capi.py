@@ -97,6 +97,7 @@ PROTOTYPES = {
     "savgol_apply_halo": (C.c_int, [FP, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "savgol2d_apply_batch": (C.c_int, [F2, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int,
                                        C.c_size_t, C.c_size_t, C.c_int]),
+    "savgol2d_b200_plan": (C.c_int, [F2, C.POINTER(C.c_int), C.POINTER(C.c_float)]),
     "savgol2d_apply_band": (C.c_int, [F2, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "savgol_b200_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]),
     "savgol_b200_ipc_open": (C.c_void_p, [C.c_void_p, C.c_size_t]),

@@ -230,6 +230,15 @@ void savgol2d_destroy(Savgol2DFilter* filter)
     free(filter);
 }
 
+int savgol2d_b200_plan(const Savgol2DFilter* filter, int* rank, float* sum_err)
+{
+    Filter2DImpl* fi = filter ? live2d(filter) : nullptr;
+    if (!fi) return -1;
+    if (rank) *rank = fi->plan.rank;
+    if (sum_err) *sum_err = fi->plan.sum_err;
+    return 0;
+}
+
 int savgol2d_apply_band(const Savgol2DFilter* filter, const float* input, int rows, int cols, int in_stride, float* output,
                         int out_stride, Savgol2DBoundary boundary, int top_halo, int bottom_halo)
 {

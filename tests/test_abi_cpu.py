@@ -163,3 +163,47 @@ def test_reference_export_tool_on_our_library_emits_identical_header(tmp_path):
                            stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         strip = lambda p: [l for l in open(p).read().splitlines() if "enerated" not in l]
         assert strip(a) == strip(b), (n, m, d)
+
+
+def test_2d_fast_path_covers_the_configuration_space():
+    # host-only: every valid 2D filter (square and rectangular windows up to 33x33, orders 0..6, derivatives
+    # up to 2+2) must get a separable plan within the acceptance bound -- a rejected plan would silently send
+    # that filter to the literal window kernel (14x slower)
+    import ctypes as C
+    import savgol_b200 as sg
+    lib = sg.lib()
+    total, rejected, worst, ranks = 0, [], 0.0, {}
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(2)
+    os.dup2(devnull, 2)          # invalid windows print the reference's "weight computation failed" line
+    try:
+        for n in range(1, 17):
+            for order in range(0, 7):
+                for dx in range(0, 3):
+                    for dy in range(0, 3):
+                        if dx + dy > order:
+                            continue
+                        for nx, ny in ((n, n), (n, max(1, n // 2))):
+                            cfg = sg._capi.Savgol2DConfig(nx, ny, order, dx, dy, 1.0, 1.0)
+                            if not lib.savgol2d_config_valid(C.byref(cfg)):
+                                continue
+                            h = lib.savgol2d_create(C.byref(cfg))
+                            if not h:
+                                continue
+                            r, e = C.c_int(), C.c_float()
+                            assert lib.savgol2d_b200_plan(h, C.byref(r), C.byref(e)) == 0
+                            total += 1
+                            ranks[r.value] = ranks.get(r.value, 0) + 1
+                            if r.value == 0:
+                                rejected.append((nx, ny, order, dx, dy))
+                            else:
+                                worst = max(worst, e.value)
+                            lib.savgol2d_destroy(h)
+    finally:
+        os.dup2(saved, 2)
+        os.close(devnull)
+        os.close(saved)
+    assert total > 1000
+    assert len(rejected) <= total // 100, rejected[:20]
+    assert worst <= 4e-7, worst
+    assert set(ranks) <= {0, 1, 2, 3, 4}
