@@ -47,6 +47,11 @@ for nx, ny, o, dx, dy in [(2, 2, 2, 0, 0), (7, 7, 3, 0, 0), (7, 7, 3, 1, 0), (12
         for shape in [(2 * ny + 3, 2 * nx + 9), (150, 300), (2, 70, 260), (333, 131), (1, 600, 64)]:
             img = torch.from_numpy(rng.random(shape).astype(np.float32)).cuda()
             f2.apply(img, b)
+fb = sg.Savgol2DFilter(7, 7, 3)
+imgb = torch.from_numpy(rng.random((300, 260)).astype(np.float32)).cuda()
+fb.apply_band(imgb[0:107], 0, 7, "reflect")          # top band (image border above), neighbour rows below
+fb.apply_band(imgb[93:207], 7, 7, "constant")        # interior band
+fb.apply_band(imgb[193:300], 7, 0, "constant")       # bottom band
 sg.set_exact(True)
 f2 = sg.Savgol2DFilter(3, 2, 3)
 f2.apply(torch.from_numpy(rng.random((40, 50)).astype(np.float32)).cuda(), "reflect")
