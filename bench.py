@@ -1,26 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the B200-native Savitzky-Golay engine.
+"""bench.py -- benchmark of the B200-native Savitzky-Golay engine.
 
 Metric (BASELINE.json): Gsamples/s and fraction of the HBM roofline of the 1D batch filter.
-Workload at every N (BASELINE.json configs[1], "c2"): 65,536 signals x 4,096 samples fp32,
-half_window 16, poly_order 3, derivative 1, REFLECT boundary -- PER GPU (weak scaling: the batch
-of independent signals is sharded with no collective, each rank filters its own 65,536 signals).
+Headline workload at every N (BASELINE.json configs[1], "c2"): 65,536 signals x 4,096 samples fp32,
+half_window 16, poly_order 3, derivative 1, REFLECT boundary -- PER GPU (weak scaling: the batch of
+independent signals is sharded with no collective, each rank filters its own 65,536 signals).
 
-One step = one pass of the hot path over the whole per-GPU batch = one launch of sg1d_kernel
-through the C ABI (savgol_apply_batch) on device-resident buffers (1 GiB in + 1 GiB out, far
-larger than the 126 MB L2, so no explicit L2 flush is needed between steps).
+One step = one pass of the hot path over the whole per-GPU batch = one kernel launch through the C ABI
+(savgol_apply_batch) on device-resident buffers (1 GiB in + 1 GiB out, far larger than the 126 MB L2, so no
+explicit L2 flush is needed between steps).
 
-JSON line keys: see the task contract.  `value` = device-resident throughput (CUDA events, max
-over ranks); `e2e` = the same call with pinned HOST buffers, H2D + D2H inside the timed region;
-`roofline` = algorithmic bytes (8 B/sample) / kernel time vs the measured HBM peak;
-`cpu_baseline` = the unmodified reference C code (oracle/_ref) on all host cores.
+The default invocation also runs the other BASELINE configs after the headline and attaches them to the
+same JSON line under "configs": c1 (one 1M-sample signal), c3 (one 2^29-sample slice per GPU of a single
+periodic signal; at N > 1 the n-sample halos are read from the ring neighbours' HBM over NVLink inside the
+kernel, parity checked on EVERY rank at both seams), c5 (multichannel chunked stream), c4 (savgol2d, 256
+images of 4096^2).  Each record carries value, ms_per_step, both rooflines (HBM and fp32 pipe), parity,
+a `sustained` sub-record (seconds of back-to-back launches with clocks / power), `e2e` (the C-ABI call on
+pinned HOST buffers, copies inside the timed region) and, at N = 1, `cpu_baseline` (the unmodified reference
+on the box's host cores).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c1|c3|c5|c4]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload all|c1|c2|c3|c4|c5]
 """
 from __future__ import annotations
 
 import argparse
-import ctypes as C
 import json
 import os
 import statistics
@@ -48,6 +51,17 @@ WORKLOADS = {
     "c4": dict(kind="2d", images=256, rows=4096, cols=4096, nx=7, ny=7, order=3, boundary="constant",
                desc="savgol2d: 256 images of 4096x4096 per GPU, 15x15 window, order 3, constant boundary"),
 }
+ORDER = ["c2", "c1", "c3", "c5", "c4"]
+
+
+def config_of(name):
+    """Static description of a workload -- identical in both arms (the driver compares them)."""
+    wl = WORKLOADS[name]
+    big = name != "c1"
+    return {"workload": wl["desc"],
+            "l2": "inputs larger than L2 (no flush needed)" if big else "L2 flushed between steps by a 256 MiB fill",
+            "sharding": "contiguous slices of one signal per rank, n-sample halos from the ring neighbours" if wl["kind"] == "long"
+            else "independent units per rank, no collective"}
 
 
 def measured_peaks():
@@ -96,6 +110,7 @@ class ClockSampler:
     def start(self):
         if self.nv is None:
             return
+        self.samples = []
         self.stop_flag = False
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
@@ -121,95 +136,79 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-def make_batch_numpy(rows, length, seed, np):
-    """Seeded synthetic batch: N(0,1) noise + a per-signal sinusoid."""
-    rng = np.random.default_rng(seed)
-    x = rng.standard_normal((rows, length), dtype=np.float32)
-    t = np.arange(length, dtype=np.float32)
-    amp = rng.uniform(0.5, 2.0, (rows, 1)).astype(np.float32)
-    frq = rng.uniform(0.002, 0.05, (rows, 1)).astype(np.float32)
-    x += amp * np.sin(frq * t[None, :])
-    return x
-
-
-def cpu_reference_rate(wl, nthreads, reps=2, rows_cap=None):
-    """Times the unmodified reference (oracle/_ref) -- or the oracle port when it is absent -- over
-    independent signals on `nthreads` host threads.  Returns (Gsamples/s, kind, sample description)."""
-    import numpy as np
-    from oracle import oracle as O
-    rows = wl["rows"] if rows_cap is None else min(wl["rows"], rows_cap)
-    L = wl["length"]
-    x = make_batch_numpy(rows, L, 1, np)
-    y = np.empty_like(x)
-    lib = O.lib()
-    if O.have_ref():
-        R = O.ref()
-        cfg = O.make_config(wl["n"], wl["m"], wl["d"], wl["dt"], wl["boundary"])
-        f = R.savgol_create(C.byref(cfg))
-        run = lambda: lib.sgh_apply_rows(O.fnptr(R, "savgol_apply"), C.cast(f, C.c_void_p), O._fp(x), O._fp(y),
-                                         rows, L, L, L, nthreads)
-        kind = "reference"
-    else:
-        of = O.Filter1D(wl["n"], wl["m"], wl["d"], wl["dt"], wl["boundary"])
-        import concurrent.futures as cf
-        pool = cf.ThreadPoolExecutor(nthreads)
-        step = (rows + nthreads - 1) // nthreads
-
-        def part(i):
-            a, b = i * step, min(rows, (i + 1) * step)
-            if a < b:
-                lib.sgo_apply_batch(of.n, O._fp(of.center), O._fp(of.edge), of.dt_inv, of.mode,
-                                    x[a:b].ctypes.data_as(O.f32p), y[a:b].ctypes.data_as(O.f32p), b - a, L, L, L)
-        run = lambda: list(pool.map(part, range(nthreads)))
-        kind = "port"
-    run()  # warm (page faults, thread start)
-    best = float("inf")
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        run()
-        best = min(best, time.perf_counter() - t0)
-    rate = rows * L / best / 1e9
-    sample = f"{rows}x{L} signals ({'full per-GPU workload' if rows == wl['rows'] else 'subset'}), best of {reps}, " \
-             f"gcc -O2 -ffp-contract=off, {nthreads} threads over independent signals"
-    return rate, kind, sample, (x, y)
-
-
 def run_reference_arm(args, rank, world):
+    """The reference's own CPU implementation on the box's host cores (oracle/_ref = the unmodified reference
+    compiled from its sources; the oracle port only where that is absent).  Rank 0 alone works."""
     if rank != 0:
         return
-    wl = WORKLOADS[args.workload]
-    if wl["kind"] != "batch":
-        print(json.dumps({"impl": "reference", "unavailable": "reference arm implemented for the 1D batch workloads"}))
-        return
+    from bench_workloads import cpu_rate
+    names = ORDER if args.workload == "all" else [args.workload]
     nthreads = os.cpu_count() or 1
-    # each step is one pass over a bounded sample so that steps+warmup stay within minutes
-    rows_cap = max(256, min(wl["rows"], int(4e8 // wl["length"] // max(1, args.steps + args.warmup) * 4)))
-    import numpy as np  # noqa: F401
-    rate, kind, sample, _ = cpu_reference_rate(wl, nthreads, reps=max(1, args.steps), rows_cap=rows_cap)
-    rows = min(wl["rows"], rows_cap)
+    recs = {}
+    for name in names:
+        wl = WORKLOADS[name]
+        # each step is one pass over a bounded sample so that steps + warmup stay within minutes
+        budget = 1.0 if name == names[0] else 0.5
+        rate, kind, sample, units = cpu_rate(wl, nthreads, reps=max(1, min(args.steps, 3)), budget=budget)
+        recs[name] = {"value": round(rate, 4), "unit": UNIT, "cores": nthreads, "kind": kind, "sample": sample,
+                      "ms_per_pass": round(units / rate / 1e6, 3)}
+    head = names[0]
+    r = recs[head]
     line = {
-        "impl": "reference", "metric": METRIC, "value": round(rate, 4), "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(rows * wl["length"] / rate / 1e6, 3),
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_pass"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "step": sample},
-        "cpu_baseline": {"value": round(rate, 4), "unit": UNIT, "cores": nthreads, "kind": kind, "sample": sample},
-        "e2e": {"value": round(rate, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": config_of(head),
+        "cpu_baseline": r,
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if len(names) > 1:
+        line["configs"] = {n: {"value": recs[n]["value"], "unit": UNIT, "config": config_of(n), "cpu_baseline": recs[n],
+                               "e2e": {"value": recs[n]["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                           for n in names[1:]}
     print(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------------
+def record_of(name, res, world, peaks, peak_kind, traffic, steps, warmup):
+    from bench_workloads import FP32_PEAK_TFMA
+    units_per_step = res["units_per_step_per_rank"] * world
+    ms = res["ms_per_step"]
+    value = units_per_step / (ms * 1e-3) / 1e9
+    kern_ms = res["kernel_ms"]
+    alg_bytes = res["alg_bytes_per_launch"]
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    tfma = res["fp32_ops_per_unit"] * res["units_per_step_per_rank"] / (kern_ms * 1e-3) / 1e12
+    rec = {
+        "value": round(value, 3), "unit": UNIT, "steps": res.get("steps", steps), "warmup": warmup, "ms_per_step": round(ms, 5),
+        "config": dict(config_of(name), **res.get("config", {})),
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": traffic, "peak_kind": peak_kind,
+                     "kernel": res["kernel"], "kernel_ms": round(kern_ms, 5), "alg_bytes_per_launch": alg_bytes,
+                     "fp32": {"tfma_s": round(tfma, 2), "peak": FP32_PEAK_TFMA, "frac": round(tfma / FP32_PEAK_TFMA, 4),
+                              "ops_per_unit": res["fp32_ops_per_unit"],
+                              "peak_kind": "FFMA lane-operations/s, tools/microbench.cu on B200 at 1965 MHz"}},
+        "clocks": res["clocks"],
+        "gpu_launches": res["gpu_launches"], "tma_launches": res.get("tma_launches"),
+        "parity": res.get("parity"),
+    }
+    for k in ("sustained", "e2e", "cpu_baseline"):
+        if res.get(k):
+            rec[k] = res[k]
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="all", choices=["all"] + sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sustained", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -224,9 +223,11 @@ def main():
     import torch
     import torch.distributed as dist
     import savgol_b200 as sg
+    from bench_workloads import Ctx, bind_near_gpu, run_1d_family, run_2d
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    numa = bind_near_gpu(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -243,50 +244,44 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    wl = WORKLOADS[args.workload]
     lib = sg.lib()
-    traffic = None
-    try:  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get("bytes")
+    try:  # DRAM bytes per launch of the dominant kernels, from the committed ncu --set full captures
+        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
-        pass
+        traffic_tab = {}
     peaks, peak_kind = measured_peaks()
-    sampler = ClockSampler(local)
-    extra = {}
+    ctx = Ctx(torch=torch, np=np, lib=lib, sg=sg, dev=dev, rank=rank, world=world, local=local, dist=dist, barrier=barrier,
+              max_over_ranks=max_over_ranks, sampler=ClockSampler(local), sampler_cls=ClockSampler, peaks=peaks)
 
-    if wl["kind"] in ("batch", "long", "stream"):
-        from bench_workloads import run_1d_family
-        res = run_1d_family(wl, args, sg, lib, torch, np, dev, rank, world, barrier, max_over_ranks, sampler, dist)
-    else:
-        from bench_workloads import run_2d
-        res = run_2d(wl, args, sg, lib, torch, np, dev, rank, world, barrier, max_over_ranks, sampler, dist)
+    names = ORDER if args.workload == "all" else [args.workload]
+    recs = {}
+    for i, name in enumerate(names):
+        wl = WORKLOADS[name]
+        head = i == 0
+        steps = args.steps if head else max(3, min(args.steps, 10))
+        sustain = 0.0 if args.no_sustained else (2.0 if name in ("c2", "c4") else 1.0)
+        want_cpu = world == 1 and rank == 0 and not args.no_cpu
+        fn = run_2d if wl["kind"] == "2d" else run_1d_family
+        res = fn(wl, ctx, steps, args.warmup, not args.no_e2e, want_cpu, sustain)
+        if rank == 0:
+            recs[name] = record_of(name, res, world, peaks, peak_kind, traffic_tab.get(name, {}).get("bytes"), steps, args.warmup)
+        del res
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
 
     if rank == 0:
-        units_per_step = res["units_per_step_per_rank"] * world
-        ms = res["ms_per_step"]
-        value = units_per_step / (ms * 1e-3) / 1e9
-        kern_ms = res["kernel_ms"]
-        alg_bytes = res["alg_bytes_per_launch"]
-        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-        line = {
-            "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(ms, 5), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict({"workload": wl["desc"], "l2": "inputs larger than L2 (no flush needed)" if res["bytes_in"] > 2e8
-                            else "L2 flushed between steps by a 256 MiB memset", "sharding": "independent units per rank, no collective"
-                            if wl["kind"] != "long" else "contiguous slices of one signal per rank"}, **res.get("config", {})),
-            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": res.get("traffic", traffic), "peak_kind": peak_kind,
-                         "kernel": res["kernel"], "kernel_ms": round(kern_ms, 5), "alg_bytes_per_launch": alg_bytes},
-            "clocks": res["clocks"],
-            "gpu_launches": res["gpu_launches"],
-            "parity": res.get("parity"),
-        }
-        if res.get("e2e"):
-            line["e2e"] = res["e2e"]
-        if res.get("cpu_baseline"):
-            line["cpu_baseline"] = res["cpu_baseline"]
-        line.update(extra)
+        head = recs[names[0]]
+        line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic"}
+        for k, v in head.items():
+            if k not in ("value", "unit", "steps", "warmup", "ms_per_step"):
+                line[k] = v
+        if numa is not None:
+            line["numa_node"] = numa
+        if len(names) > 1:
+            line["configs"] = {n: recs[n] for n in names[1:]}
+            line["gpu_launches_all_configs"] = sum(r["gpu_launches"] for r in recs.values())
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -235,6 +235,11 @@ void savgol_b200_set_stream(void *cuda_stream);
 void *savgol_b200_get_stream(void);
 /* Number of kernel launches issued by this library in this process so far. */
 unsigned long long savgol_b200_launch_count(void);
+/* ... of which launches of the bulk-tensor (TMA) 1D kernels (contiguous 16-byte aligned rows of >= 1024
+ * samples, default arithmetic); SAVGOL_B200_NO_TMA=1 in the environment routes them to the cp.async kernels. */
+unsigned long long savgol_b200_tma_launch_count(void);
+/* Experiment / test switch for the above (process-wide; default on). */
+void savgol_b200_set_tma(int on);
 /* Arithmetic flavour: 0 (default) = FMA chains, within 1e-6*max|x|/dt^d of the
  * reference; 1 = "exact": the reference's own summation order with unfused
  * multiply/add, bit-identical to the reference C code (slower; for verification). */
@@ -287,6 +292,10 @@ int savgol2d_apply_batch(const Savgol2DFilter *filter,
  * (column factor x row factor) terms, 0 if the weight table was not accepted (every apply then runs the
  * literal window kernel); *sum_err = sum |W - sum_r col_r x row_r| over the table.  Host only.  0 / -1. */
 int savgol2d_b200_plan(const Savgol2DFilter *filter, int *rank, float *sum_err);
+/* Which kernel family the plan selects: 0 literal window (sg2d_direct.cu), 1 rank-R separable factors
+ * (sg2d_sep.cu), 2 additive surface W = u(x) + v(y) with box-sum factors (sg2d_add.cu; every order-2/3
+ * smoothing filter with a square window up to 17x17).  -1 when `filter` was not made by savgol2d_create. */
+int savgol2d_b200_plan_kind(const Savgol2DFilter *filter);
 
 /* One horizontal band of a larger image (row-band sharding of a single huge image over several
  * GPUs; device pointers).  `input` is a buffer of `rows` rows: `top_halo` rows that precede the
@@ -299,6 +308,14 @@ int savgol2d_apply_band(const Savgol2DFilter *filter,
                         const float *input, int rows, int cols, int in_stride,
                         float *output, int out_stride, Savgol2DBoundary boundary,
                         int top_halo, int bottom_halo);
+/* The same with the position of the band in its image: `image_row0` = image row of the first row of `input`
+ * (halo rows included).  The additive 2D kernel sums an output row's terms in an order that depends on the
+ * parity of its image row; telling it where the band sits makes every pixel round exactly as in a whole-image
+ * call, so bands computed by different GPUs reassemble the whole-image result bit for bit. */
+int savgol2d_apply_band_at(const Savgol2DFilter *filter,
+                           const float *input, int rows, int cols, int in_stride,
+                           float *output, int out_stride, Savgol2DBoundary boundary,
+                           int top_halo, int bottom_halo, int image_row0);
 
 /* Multi-channel chunked stream ------------------------------------------- */
 

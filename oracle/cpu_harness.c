@@ -30,8 +30,11 @@ typedef int (*sgh_stream_init_fn)(void *stream, const void *filter);
 typedef int (*sgh_stream_push_full_fn)(void *stream, float x, float *out, int max_out);
 typedef int (*sgh_stream_flush_fn)(void *stream, float *out, int max_out);
 
+/* ref: include/iterative/savgolFilter.h:201-203 */
+typedef size_t (*sgh_valid_fn)(const void *filter, const float *in, size_t in_len, float *out);
+
 typedef struct {
-    int kind; /* 0 rows, 1 images, 2 stream channels */
+    int kind; /* 0 rows, 1 images, 2 stream channels, 3 chunks of one long signal (VALID) */
     void *fn, *fn2, *fn3;
     const void *filter;
     const float *in;
@@ -55,6 +58,16 @@ static void *sgh_worker(void *arg)
         for (size_t r = j->begin; r < j->end; ++r)
             if (f(j->filter, j->in + r * j->ipitch, j->rows, j->cols, j->cols,
                   j->out + r * j->opitch, j->cols, j->boundary)) j->rc = -1;
+    } else if (j->kind == 3) {
+        /* chunk c = outputs [c*len, min((c+1)*len, total)) of one long signal; j->in is the signal with n
+         * samples of context on either side (j->rows = n, j->ipitch = total outputs) */
+        sgh_valid_fn f = (sgh_valid_fn)j->fn;
+        const size_t n = (size_t)j->rows, total = j->ipitch;
+        for (size_t c = j->begin; c < j->end; ++c) {
+            const size_t o = c * j->len;
+            const size_t l = o + j->len <= total ? j->len : total - o;
+            if (f(j->filter, j->in + o, l + 2 * n, j->out + o) != l) j->rc = -1;
+        }
     } else {
         /* one SavgolStream (296 B in the reference ABI) per channel, on the stack */
         sgh_stream_init_fn init = (sgh_stream_init_fn)j->fn;
@@ -129,4 +142,17 @@ int sgh_stream_channels(void *init_fn, void *push_full_fn, void *flush_fn, const
     p.kind = 2; p.fn = init_fn; p.fn2 = push_full_fn; p.fn3 = flush_fn; p.filter = filter;
     p.in = in; p.out = out; p.len = len; p.ipitch = ipitch; p.opitch = opitch; p.flush = flush;
     return sgh_run(p, channels, nthreads);
+}
+
+/* One long signal through the reference's VALID path (size_t-clean, ref: src/savgolFilter.c:821-850), cut into
+ * chunks of `chunk` outputs that run on `nthreads` threads.  `in` holds n samples of context before and after
+ * the `total` output positions (for a PERIODIC signal: the wrap-padded signal -- SURVEY.md Q6: periodic ==
+ * VALID over the wrap-padded signal, bit for bit). */
+int sgh_valid_chunks(void *valid_fn, const void *filter, const float *in, float *out, size_t total,
+                     int half_window, size_t chunk, int nthreads)
+{
+    sgh_job p = {0};
+    p.kind = 3; p.fn = valid_fn; p.filter = filter; p.in = in; p.out = out;
+    p.len = chunk; p.ipitch = total; p.rows = half_window;
+    return sgh_run(p, (total + chunk - 1) / chunk, nthreads);
 }

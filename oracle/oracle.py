@@ -76,6 +76,7 @@ def lib() -> C.CDLL:
         L.sgh_stream_channels.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, f32p, f32p,
                                           C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int,
                                           C.c_int]
+        L.sgh_valid_chunks.argtypes = [C.c_void_p, C.c_void_p, f32p, f32p, C.c_size_t, C.c_int, C.c_size_t, C.c_int]
         _lib = L
     return _lib
 

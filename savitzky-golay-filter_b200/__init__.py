@@ -376,16 +376,17 @@ class Savgol2DFilter:
             raise RuntimeError("savgol2d_apply_valid failed")
         return out
 
-    def apply_band(self, buf, top_halo, bottom_halo, boundary="constant", out=None):
+    def apply_band(self, buf, top_halo, bottom_halo, boundary="constant", out=None, image_row0=0):
         """One horizontal band of a larger image: ``buf`` = [top_halo rows | band | bottom_halo rows] (device
-        tensor); a halo of 0 rows marks an image border.  Returns the filtered band rows."""
+        tensor); a halo of 0 rows marks an image border; ``image_row0`` = image row of buf[0] (makes the band
+        round exactly like the whole-image call).  Returns the filtered band rows."""
         xp, _k, _ = _prep(buf)
         rows, cols = buf.shape
         if out is None:
             out = _empty_like(buf, (rows - top_halo - bottom_halo, cols))
         op, _ko, _ = _prep(out, "output")
-        rc = lib().savgol2d_apply_band(self._h, xp, rows, cols, _row_pitch(buf), op, _row_pitch(out), BOUNDARY_2D[boundary],
-                                       int(top_halo), int(bottom_halo))
+        rc = lib().savgol2d_apply_band_at(self._h, xp, rows, cols, _row_pitch(buf), op, _row_pitch(out), BOUNDARY_2D[boundary],
+                                          int(top_halo), int(bottom_halo), int(image_row0))
         if rc != 0:
             raise RuntimeError("savgol2d_apply_band failed (see stderr)")
         return out

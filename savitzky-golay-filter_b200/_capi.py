@@ -91,6 +91,8 @@ PROTOTYPES = {
     "savgol_b200_set_stream": (None, [C.c_void_p]),
     "savgol_b200_get_stream": (C.c_void_p, []),
     "savgol_b200_launch_count": (C.c_ulonglong, []),
+    "savgol_b200_tma_launch_count": (C.c_ulonglong, []),
+    "savgol_b200_set_tma": (None, [C.c_int]),
     "savgol_b200_set_exact": (None, [C.c_int]),
     "savgol_b200_get_exact": (C.c_int, []),
     "savgol_apply_batch": (C.c_int, [FP, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t]),
@@ -98,7 +100,9 @@ PROTOTYPES = {
     "savgol2d_apply_batch": (C.c_int, [F2, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int,
                                        C.c_size_t, C.c_size_t, C.c_int]),
     "savgol2d_b200_plan": (C.c_int, [F2, C.POINTER(C.c_int), C.POINTER(C.c_float)]),
+    "savgol2d_b200_plan_kind": (C.c_int, [F2]),
     "savgol2d_apply_band": (C.c_int, [F2, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "savgol2d_apply_band_at": (C.c_int, [F2, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "savgol_b200_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]),
     "savgol_b200_ipc_open": (C.c_void_p, [C.c_void_p, C.c_size_t]),
     "savgol_b200_ipc_close": (C.c_int, [C.c_void_p, C.c_size_t]),

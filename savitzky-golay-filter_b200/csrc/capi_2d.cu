@@ -21,7 +21,7 @@ struct Filter2DImpl {
     Savgol2DFilter pub;  // public ABI prefix (ref: include/iterative/savgol2d.h:95-103)
     uint64_t magic;
     float* d_weights[sge::kMaxDevices];
-    sg2d::SepPlan plan;  // separable factorisation of the weight surface (sg2d_sep.cu)
+    sg2d::SepPlan plan;  // separable / additive factorisation of the weight surface (factor2d.cpp)
 };
 constexpr uint64_t kMagic2D = 0x5347423230303244ULL;
 
@@ -64,7 +64,7 @@ const float* weights_device(const Savgol2DFilter* f, cudaStream_t st, float** te
 // One launch over device-resident images.
 bool run2d_device(const Savgol2DFilter* f, const float* in, int rows, int cols, long long is, long long ipitch,
                   float* out, long long os, long long opitch, long long n_images, int boundary, cudaStream_t st,
-                  int top_halo = -1, int bottom_halo = -1)
+                  int top_halo = -1, int bottom_halo = -1, int image_row0 = 0)
 {
     const int nx = f->config.half_window_x, ny = f->config.half_window_y;
     sg2d::Args2D a{};
@@ -81,6 +81,7 @@ bool run2d_device(const Savgol2DFilter* f, const float* in, int rows, int cols, 
         // produced; a side without halo is a true image border and follows the boundary rule
         a.out_rows = rows - top_halo - bottom_halo; a.out_cols = cols;
         a.cy = top_halo; a.cx = 0;
+        a.row0 = image_row0;
     } else if (boundary == sg2d::B_VALID) {
         a.out_rows = rows - 2 * ny; a.out_cols = cols - 2 * nx;
         a.cy = ny; a.cx = nx;
@@ -239,8 +240,21 @@ int savgol2d_b200_plan(const Savgol2DFilter* filter, int* rank, float* sum_err)
     return 0;
 }
 
+int savgol2d_b200_plan_kind(const Savgol2DFilter* filter)
+{
+    Filter2DImpl* fi = filter ? live2d(filter) : nullptr;
+    if (!fi) return -1;
+    return fi->plan.rank < 1 ? 0 : fi->plan.additive ? 2 : 1;
+}
+
 int savgol2d_apply_band(const Savgol2DFilter* filter, const float* input, int rows, int cols, int in_stride, float* output,
                         int out_stride, Savgol2DBoundary boundary, int top_halo, int bottom_halo)
+{
+    return savgol2d_apply_band_at(filter, input, rows, cols, in_stride, output, out_stride, boundary, top_halo, bottom_halo, 0);
+}
+
+int savgol2d_apply_band_at(const Savgol2DFilter* filter, const float* input, int rows, int cols, int in_stride, float* output,
+                           int out_stride, Savgol2DBoundary boundary, int top_halo, int bottom_halo, int image_row0)
 {
     if (!filter || !input || !output) return -1;
     const int ny = filter->config.half_window_y;
@@ -265,7 +279,7 @@ int savgol2d_apply_band(const Savgol2DFilter* filter, const float* input, int ro
         return -1;
     }
     return run2d_device(filter, input, rows, cols, in_stride, 0, output, out_stride, 0, 1, static_cast<int>(boundary),
-                        sge::current_stream(), top_halo, bottom_halo) ? 0 : -1;
+                        sge::current_stream(), top_halo, bottom_halo, image_row0) ? 0 : -1;
 }
 
 int savgol2d_apply_batch(const Savgol2DFilter* filter, const float* input, int rows, int cols, int in_stride,

@@ -9,7 +9,7 @@
 
 #include "sg1d_launch.h"
 
-namespace sg { extern std::atomic<unsigned long long> g_launches; }
+namespace sg { extern std::atomic<unsigned long long> g_launches, g_tma_launches; extern std::atomic<int> g_tma_enabled; }
 
 namespace sge {
 
@@ -239,6 +239,8 @@ int savgol_b200_device_ok(void) { return sge::device_ready(false) ? 1 : 0; }
 void savgol_b200_set_stream(void* s) { sge::t_stream = static_cast<cudaStream_t>(s); }
 void* savgol_b200_get_stream(void) { return sge::t_stream; }
 unsigned long long savgol_b200_launch_count(void) { return sg::g_launches.load(); }
+unsigned long long savgol_b200_tma_launch_count(void) { return sg::g_tma_launches.load(); }
+void savgol_b200_set_tma(int on) { sg::g_tma_enabled.store(on ? 1 : 0); }
 void savgol_b200_set_exact(int exact) { sge::g_exact.store(exact ? 1 : 0); }
 int savgol_b200_get_exact(void) { return sge::g_exact.load(); }
 

@@ -12,6 +12,7 @@
 // table the reference would use to well below the parity tolerance.  The device kernel
 // (sg2d_sep.cu) then needs (2nx+1)+(2ny+1) MACs per pixel and factor instead of their product.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -154,6 +155,45 @@ void plan_separable(int nx, int ny, int order, const double* coef, const float* 
     plan->parity_y = py;
     (void)sum_abs;
     if (err_sum <= 4e-7) plan->rank = rank;
+
+    // Additive surfaces: W(y,x) = u(x) + v(y).  The total-degree <= 3 fits evaluated at the window centre
+    // (smoothing, d2/dx2, d2/dy2, their sum) only contain 1, x^2, y^2, so the rank-2 table is a sum of two
+    // one-variable functions and both "other" factors are constant 1 -- box sums for the kernel
+    // (sg2d_add.cu).  The constant is split so that v vanishes at the window ends (two taps less).
+    static const bool no_additive = [] { const char* e = std::getenv("SAVGOL_B200_NO_ADDITIVE"); return e && e[0] == '1'; }();
+    if (rank == 2 && px == 1 && py == 1 && nx == ny && nx <= 8 && !no_additive) {
+        const double wcc = W[static_cast<size_t>(ny) * ww + nx];
+        double dev = 0.0;
+        for (int y = 0; y < wh; ++y)
+            for (int x = 0; x < ww; ++x)
+                dev = std::fmax(dev, std::fabs(W[static_cast<size_t>(y) * ww + x] -
+                                               (W[static_cast<size_t>(ny) * ww + x] + W[static_cast<size_t>(y) * ww + nx] - wcc)));
+        if (dev <= 1e-12 * wmax) {
+            float u[33], v[33];
+            const double v_end = W[nx];   // W(y = -ny, x = 0)
+            for (int x = 0; x < ww; ++x) u[x] = static_cast<float>(W[static_cast<size_t>(ny) * ww + x] - wcc + v_end);
+            for (int y = 0; y < wh; ++y) v[y] = static_cast<float>(W[static_cast<size_t>(y) * ww + nx] - v_end);
+            v[0] = v[wh - 1] = 0.0f;
+            double esum = 0.0, emax = 0.0;
+            for (int y = 0; y < wh; ++y)
+                for (int x = 0; x < ww; ++x) {
+                    const double d = std::fabs(static_cast<double>(u[x]) + static_cast<double>(v[y]) -
+                                               static_cast<double>(weights[static_cast<size_t>(y) * ww + x]));
+                    esum += d;
+                    emax = std::fmax(emax, d);
+                }
+            if (esum <= 4e-7) {
+                std::memset(plan->row, 0, sizeof(plan->row));
+                std::memset(plan->col, 0, sizeof(plan->col));
+                for (int x = 0; x < ww; ++x) plan->row[0][x] = u[x];
+                for (int y = 0; y < wh; ++y) plan->col[0][y] = v[y];
+                plan->rank = 2;
+                plan->additive = 1;
+                plan->max_err = static_cast<float>(emax / wmax);
+                plan->sum_err = static_cast<float>(esum);
+            }
+        }
+    }
 }
 
 }  // namespace sg2d

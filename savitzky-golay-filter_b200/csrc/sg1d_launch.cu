@@ -3,15 +3,18 @@
 #include "sg1d_packed.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 
 namespace sg {
 
-#define SG_DECL(g) const Kernel1D* sg1d_group_table_##g();
+#define SG_DECL(g) const Kernel1D* sg1d_group_table_##g(); const Kernel1DTma* sg1d_tma_group_table_##g();
 SG_DECL(0) SG_DECL(1) SG_DECL(2) SG_DECL(3) SG_DECL(4) SG_DECL(5) SG_DECL(6) SG_DECL(7)
 #undef SG_DECL
 
 std::atomic<unsigned long long> g_launches{0};
+std::atomic<unsigned long long> g_tma_launches{0};   // launches of the bulk-tensor (TMA) 1D kernels
+std::atomic<int> g_tma_enabled{[] { const char* e = getenv("SAVGOL_B200_NO_TMA"); return (e && e[0] == '1') ? 0 : 1; }()};
 
 const Kernel1D* sg1d_group_table(int group)
 {
@@ -28,8 +31,71 @@ const Kernel1D* sg1d_group_table(int group)
     }
 }
 
+const Kernel1DTma* sg1d_tma_group_table(int group)
+{
+    switch (group) {
+        case 0: return sg1d_tma_group_table_0();
+        case 1: return sg1d_tma_group_table_1();
+        case 2: return sg1d_tma_group_table_2();
+        case 3: return sg1d_tma_group_table_3();
+        case 4: return sg1d_tma_group_table_4();
+        case 5: return sg1d_tma_group_table_5();
+        case 6: return sg1d_tma_group_table_6();
+        case 7: return sg1d_tma_group_table_7();
+        default: return nullptr;
+    }
+}
+
 namespace {
 struct GridInfo { int blocks_per_sm = 0; };
+GridInfo g_grid_tma[kMaxN + 1][VT_COUNT];
+
+// cuTensorMapEncodeTiled, resolved at run time (the library has to load on machines without libcuda).
+typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiled encode_tiled()
+{
+    static std::atomic<EncodeTiled> s_fn{nullptr};
+    static std::atomic<int> s_state{0};   // 0 unknown, 1 ok, -1 unavailable
+    if (s_state.load(std::memory_order_acquire) == 0) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        const cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q);
+        if (e == cudaSuccess && f && q == cudaDriverEntryPointSuccess) {
+            s_fn.store(reinterpret_cast<EncodeTiled>(f), std::memory_order_release);
+            s_state.store(1, std::memory_order_release);
+        } else {
+            (void)cudaGetLastError();
+            s_state.store(-1, std::memory_order_release);
+        }
+    }
+    return s_state.load(std::memory_order_acquire) == 1 ? s_fn.load(std::memory_order_acquire) : nullptr;
+}
+
+// {32 floats, nrows, rows} view of a batch of contiguous rows, 128-byte swizzle, box of `box_rows` tensor rows.
+bool encode_rows(EncodeTiled enc, CUtensorMap* m, const void* base, unsigned long long nrows, unsigned long long rows,
+                 unsigned long long row_bytes, unsigned box_rows)
+{
+    const cuuint64_t dims[3] = {32, nrows, rows};
+    const cuuint64_t strides[2] = {128, rows > 1 ? row_bytes : nrows * 128};
+    const cuuint32_t box[3] = {32, box_rows, 1};
+    const cuuint32_t es[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// The TMA kernels take contiguous fp32 rows of at least one segment whose base and pitch are 16-byte aligned.
+bool tma_eligible(int variant, const Args1D& a)
+{
+    if (!g_tma_enabled.load(std::memory_order_relaxed) || (variant != V_BATCH_FAST && variant != V_STREAM_FAST)) return false;
+    if (a.in_stride != 4 || a.out_stride != 4 || a.len < kTile) return false;
+    if ((reinterpret_cast<uintptr_t>(a.in) | reinterpret_cast<uintptr_t>(a.out)) & 15) return false;
+    if (a.rows > 1 && ((a.in_row_bytes | a.out_row_bytes) & 15)) return false;
+    if (a.rows >= (1LL << 31) || a.len >= (1LL << 36) || a.in_row_bytes >= (1LL << 40) || a.out_row_bytes >= (1LL << 40)) return false;
+    return true;
+}
+
 GridInfo g_grid[kMaxN + 1][V_COUNT][5];  // per (n, variant, packing); filled lazily (same value on every B200)
 int g_sms[64];
 std::mutex g_mu;
@@ -44,6 +110,51 @@ static size_t packed_smem_bytes(int n, bool lead2n, int g)
     const int delta = ((lead + 3) & ~3) - lead;
     const int rpg = 32 / g, warps = kThreads / 32;
     return static_cast<size_t>(warps) * 2 * rpg * packed_slot_chunks(n, delta, g) * 16 + static_cast<size_t>(warps) * rpg * 2 * n * 4;
+}
+
+static cudaError_t sg1d_launch_tma(EncodeTiled enc, int n, int vt, const W1D& w, Args1D& a, cudaStream_t stream)
+{
+    TmaMaps maps;
+    const unsigned long long nin = static_cast<unsigned long long>(a.len) >> 5, nout = static_cast<unsigned long long>(a.out_len) >> 5;
+    if (!encode_rows(enc, &maps.in_body, a.in, nin, a.rows, a.in_row_bytes, 32) ||
+        !encode_rows(enc, &maps.in_row, a.in, nin, a.rows, a.in_row_bytes, 1))
+        return cudaErrorNotSupported;
+    a.out_tma = nout >= 32 ? 1 : 0;
+    if (a.out_tma && !encode_rows(enc, &maps.out_body, a.out, nout, a.rows, a.out_row_bytes, 32)) return cudaErrorNotSupported;
+    if (!a.out_tma) maps.out_body = maps.in_body;   // never dereferenced
+
+    const Kernel1DTma& k = sg1d_tma_group_table((n - 1) / 4)[((n - 1) % 4) * VT_COUNT + vt];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    int bps, sms;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        GridInfo& gi = g_grid_tma[n][vt];
+        if (gi.blocks_per_sm == 0) {
+            int nb = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k.kernel, kThreads, 0);
+            if (e != cudaSuccess) return e;
+            gi.blocks_per_sm = nb > 0 ? nb : 1;
+        }
+        if (dev < 64 && g_sms[dev] == 0) {
+            e = cudaDeviceGetAttribute(&g_sms[dev], cudaDevAttrMultiProcessorCount, dev);
+            if (e != cudaSuccess) return e;
+        }
+        bps = gi.blocks_per_sm;
+        sms = dev < 64 ? g_sms[dev] : 148;
+    }
+    a.tiles_per_row = (a.len + kTile - 1) / kTile;
+    a.ntiles = a.tiles_per_row * a.rows;
+    if (a.ntiles <= 0) return cudaSuccess;
+    if (a.ntiles >= (1LL << 31) - (1LL << 20)) return cudaErrorInvalidValue;
+    long long grid = static_cast<long long>(sms) * bps;
+    const long long need = (a.ntiles + kThreads / 32 - 1) / (kThreads / 32);
+    if (grid > need) grid = need;
+    k.kernel<<<static_cast<unsigned>(grid), kThreads, 0, stream>>>(w, a, maps);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    g_tma_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
 }
 
 cudaError_t sg1d_launch(int n, int variant, const W1D& w, Args1D& a, cudaStream_t stream)
@@ -64,6 +175,13 @@ cudaError_t sg1d_launch(int n, int variant, const W1D& w, Args1D& a, cudaStream_
         variant = variant == V_BATCH_FAST ? V_PACK_BATCH_FAST : V_PACK_STREAM_FAST;
     } else if (variant >= V_PACK_BATCH_FAST) {
         return cudaErrorInvalidValue;
+    }
+    a.out_tma = 0;
+    if (a.pack_g == 0 && tma_eligible(variant, a)) {
+        if (EncodeTiled enc = encode_tiled()) {
+            const cudaError_t e = sg1d_launch_tma(enc, n, variant == V_STREAM_FAST ? VT_STREAM : VT_BATCH, w, a, stream);
+            if (e != cudaErrorNotSupported) return e;   // NotSupported: the driver refused a tensor map -> generic kernel
+        }
     }
     const Kernel1D& k = sg1d_group_table((n - 1) / 4)[((n - 1) % 4) * V_COUNT + variant];
 

@@ -1,5 +1,7 @@
 // sg1d_launch.h -- host-side dispatch table of the 1D kernel instantiations.
 #pragma once
+#include <cuda.h>
+
 #include "sg_common.cuh"
 
 namespace sg {
@@ -13,9 +15,21 @@ struct Kernel1D {
     void (*kernel)(const W1D, const Args1D);  // __global__ entry
 };
 
+// Tensor maps of the TMA kernels (sg1d_tma.cuh): the batch seen as {32 floats, len / 32, rows}, SWIZZLE_128B.
+struct alignas(64) TmaMaps {
+    CUtensorMap in_body;   // box {32, 32, 1}: the 1024 samples under a segment's outputs
+    CUtensorMap in_row;    // box {32, 1, 1}: one 128-byte halo row
+    CUtensorMap out_body;  // box {32, 32, 1}
+};
+struct Kernel1DTma {
+    void (*kernel)(const W1D, const Args1D, const TmaMaps);
+};
+enum : int { VT_BATCH = 0, VT_STREAM = 1, VT_COUNT = 2 };
+
 // Defined once per instantiation group (sg1d_inst.cu compiled with -DSG_GROUP=g covers
 // half-windows 4g+1 .. 4g+4).
 const Kernel1D* sg1d_group_table(int group);
+const Kernel1DTma* sg1d_tma_group_table(int group);
 
 // Grid sizing + launch.  Returns cudaSuccess or the launch error.
 cudaError_t sg1d_launch(int n, int variant, const W1D& w, Args1D& args, cudaStream_t stream);

@@ -24,6 +24,7 @@ struct Args2D {
     long long n_images;
     int boundary;
     float scale;
+    int row0;               // image row of the buffer's first row (bands of a larger image; 0 otherwise)
     int band_rows;          // separable kernel: output rows per work item (set by the launcher)
     unsigned* counter;      // separable kernel: work-item ticket counter, zeroed in stream order before the launch
 };
@@ -42,9 +43,14 @@ struct SepPlan {
     float max_err;            // max |W - sum_r col*row| / max|W|
     float sum_err;            // sum |W - sum_r col*row|  (bounds the extra output error per unit max|image|)
     int parity_x, parity_y;   // +1: factors even in x / y, -1: odd
+    int additive;             // 1: W(y,x) = row[0][x] + col[0][y] with col[0][0] = col[0][2ny] = 0 (rank is 2, the
+                              // "1" factors are implicit); runs sg2d_add.cu.  Square windows up to 17x17 only.
 };
 void plan_separable(int nx, int ny, int order, const double* coef, const float* weights, SepPlan* plan);
 bool separable_supported(const Args2D& a, const SepPlan& plan);
 cudaError_t launch_separable(const Args2D& a, const SepPlan& plan, cudaStream_t stream);
+cudaError_t launch_additive(const Args2D& a, const SepPlan& plan, cudaStream_t stream);   // sg2d_add.cu
+// Ticket counter of one launch of the streaming kernels (sg2d_sep.cu): 4 zeroed bytes, stream ordered.
+cudaError_t acquire_counter(cudaStream_t stream, unsigned** out);
 
 }  // namespace sg2d

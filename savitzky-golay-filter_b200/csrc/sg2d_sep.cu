@@ -1,597 +1,59 @@
-// sg2d_sep.cu -- production path of the 2D filter: streaming separable stencil for sm_100a.
-//
-// Replaces the reference's 4-deep tap loop (src/savgol2d.c:417-452, 374-393).  The weight table is
-// factorised on the host as W[y][x] = sum_{r<R} col_r[y] * row_r[x] (factor2d.cpp, R <= 4, R = 2 for
-// the order-2/3 smoothing filters), all row factors even or all odd in x.
-//
-// Execution plan -- warp-autonomous, like the 1D kernel; no __syncthreads anywhere:
-//   * work item = (image, band of <= 512 output rows, strip of 32*RX output columns), handed out by an
-//     atomic ticket (edge strips first); a warp walks DOWN its strip two input rows per step.  Rows are
-//     staged by cp.async into a private ring of 8 row buffers, 6 rows ahead of the rows being consumed
-//     (~3.4 KB in flight per warp); the row index is mapped by the boundary rule (clamp / half-sample
-//     reflect), the few pad columns of the first / last strip are copied element by element from the
-//     column the rule maps them to, so the compute is boundary agnostic.
-//   * ROW PASS: each lane owns RX consecutive columns; from a register window of the staged row it
-//     forms the folded sums s_k = x[c+k] +/- x[c-k] once and evaluates the R row factors on them
-//     (n adds + R*(n+1) FMAs per pixel instead of R*(2n+1) MACs; the FMAs packed over column pairs).
-//   * COLUMN PASS, in registers: the lane keeps the partially accumulated output rows of its columns.
-//     The R values just produced are scattered into them with packed FFMA2 (column pairs packed,
-//     weight col[wy] broadcast from a uniform register), the two oldest rows are complete and are
-//     stored (one 512-byte store per warp and row).  Half-windows <= 8: a static ring of 2n+2 rows
-//     whose indices are compile-time constants per ring phase (one copy of the column pass per
-//     phase, selected by a switch; no register ever moves).  Larger half-windows: indices static
-//     inside blocks of U = 4 rows, a block ends with a register shift.
-//   => every input pixel is read from HBM once and from shared memory (RX+2n)/RX times, no
-//      intermediate image ever exists, and there is no vertical halo recomputation except the 2n
-//      warm-up rows per band.
-#include <atomic>
-#include <mutex>
-
-#include "sg2d.h"
-#include "sg_common.cuh"
-#include "sg1d_kernel.cuh"  // static_for
-
-namespace sg { extern std::atomic<unsigned long long> g_launches; }
-
-#ifndef SG2D_KU
-#define SG2D_KU 4
-#endif
-#ifndef SG2D_RXW
-#define SG2D_RXW 4
-#endif
-#ifndef SG2D_RX4
-#define SG2D_RX4 1
-#endif
-#ifndef SG2D_WIDE_MINB
-#define SG2D_WIDE_MINB 2   // resident CTAs for the widest rank-3/4 kernels (231 registers unconstrained)
-#endif
-#ifndef SG2D_RING_MAX
-#define SG2D_RING_MAX 1500   // FFMA2 in all column-pass copies of the static ring
-#endif
-#ifndef SG2D_RING
-#define SG2D_RING 1
-#endif
-#ifndef SG2D_MINB2
-#define SG2D_MINB2 3
-#endif
-#ifndef SG2D_MINB
-#define SG2D_MINB 4
-#endif
+// sg2d_sep.cu -- dispatch of the streaming separable 2D kernel (sg2d_sep_kernel.cuh) for generic rank-R
+// factorisations; the additive surfaces W = u(x) + v(y) are instantiated in sg2d_add.cu.
+#include "sg2d_sep_kernel.cuh"
 
 namespace sg2d {
 
 namespace {
 
-using sg::cp_async16;
-using sg::cp_async4;
-using sg::cp_async_commit;
-using sg::cp_async_wait;
-
-constexpr int kU = SG2D_KU;         // rows per statically indexed block
-constexpr int kRing = 8;      // staged rows per warp
-constexpr int kAhead = 6;     // prefetch distance in rows (kRing >= kAhead + 2)
-constexpr int kBandMax = 512; // output rows per work item (upper bound; the launcher shrinks it for small batches)
-constexpr int kWarps = 4;
-
-template <int R>
-struct SepW {
-    float rc[R];            // row factor, centre tap
-    float rk[R][16];        // rk[r][k-1]: weight of s_k = x[c+k] + sx * x[c-k], k = 1..n
-    float col[R][33];       // column factor * scale, col[r][wy], wy = 0..2n
-    float sx;               // +1 (even in x) / -1 (odd in x)
-};
-
-__device__ __forceinline__ int map_index(int i, int n, int boundary)
-{
-    if (boundary == B_REFLECT) {
-        if (i < 0) i = -i - 1;
-        else if (i >= n) i = 2 * n - i - 1;
-    }
-    if (i < 0) i = 0;
-    else if (i >= n) i = n - 1;
-    return i;
-}
-
-// Run f(integral_constant<I>) for the I that equals `v` (0 <= v < COUNT).
-template <class F, int... I>
-__device__ __forceinline__ void static_switch_impl(int v, F&& f, std::integer_sequence<int, I...>)
-{
-    (void)((v == I && (f(std::integral_constant<int, I>{}), true)) || ...);
-}
-template <int COUNT, class F>
-__device__ __forceinline__ void static_switch(int v, F&& f)
-{
-    static_switch_impl(v, static_cast<F&&>(f), std::make_integer_sequence<int, COUNT>{});
-}
-
-// Stores of a lane whose columns straddle the stored region or whose row is not vector-aligned.
-template <int RX>
-__device__ __noinline__ void emit_ragged(float* dst_row, const float2 (&v)[RX / 2], int X, int Xlo, int Xhi)
-{
-#pragma unroll
-    for (int j = 0; j < RX; ++j)
-        if (X + j >= Xlo && X + j < Xhi) dst_row[j] = (j & 1) ? v[j / 2].y : v[j / 2].x;
-}
-
-__device__ __forceinline__ void cp_async4_s(unsigned smem_dst, const void* gsrc)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
-}
-
-__device__ __forceinline__ void cp_async16_s(unsigned smem_dst, const void* gsrc)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
-}
-
-
-// Pad columns of an edge strip, two rows: pad element q of the slot (the nl columns left of the image,
-// then those right of it) is copied from the column the boundary rule maps it to.  d = shared address of
-// the slot's first float (row t), r0 / r1 = start of the two source rows.  Out of line to keep the main
-// loop inside the instruction cache.
-__device__ __noinline__ void stage_pads(unsigned d, const float* r0, const float* r1, int row_bytes, int npad, int nl, int xb, int cols,
-                                        int boundary, int lane)
-{
-#pragma unroll 1
-    for (int q = lane; q < npad; q += 32) {
-        const int x = q < nl ? xb + q : cols + (q - nl);
-        const int m = map_index(x, cols, boundary);
-        const unsigned dd = d + 4 * (x - xb);
-        cp_async4_s(dd, r0 + m);
-        cp_async4_s(dd + row_bytes, r1 + m);
-    }
-}
-
-// Two rows of an EDGE STRIP (first / last strip of the image), or of an image whose rows are not 16-byte
-// aligned, into two consecutive ring slots: chunks that lie inside the image and are aligned are copied
-// 16 bytes at a time, everything else element by element (pad columns from the column the boundary rule
-// maps them to).  r0 / r1 = start of the (already mapped) source rows, d = this
-// lane's shared address in the first slot, xb = image column of the slot's first float.  Out of line:
-// 1/16 of the items of a 4096^2 image take it, it must not bloat the main loop.
-template <int ROWCH, int ROWF>
-__device__ __noinline__ void stage_edge_pair(unsigned d, const float* r0, const float* r1, int xb, int cols, int boundary, int lane)
-{
-#pragma unroll
-    for (int c0 = 0; c0 < ROWCH; c0 += 32) {
-        const int c = c0 + lane;
-        if (c0 + 32 <= ROWCH || c < ROWCH) {
-            const int xin = xb + 4 * c;
-            const bool inside = xin >= 0 && xin + 3 < cols;
-#pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                const float* r = rr ? r1 : r0;
-                const unsigned dd = d + rr * (ROWF * 4) + 16 * c0;
-                if (inside && (reinterpret_cast<uintptr_t>(r + xin) & 15) == 0) {
-                    cp_async16_s(dd, r + xin);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) cp_async4_s(dd + 4 * e, r + (inside ? xin + e : map_index(xin + e, cols, boundary)));
-                }
-            }
-        }
-    }
-}
-
-template <int N, int R, int RX>
-__global__ void __launch_bounds__(kWarps * 32, RX >= 4 ? ((N <= 6 || (N == 7 && (R == 2 || R == 3))) ? SG2D_MINB : 3) : ((N >= 15 && R >= 3) ? SG2D_WIDE_MINB : SG2D_MINB2)) sep_kernel(const __grid_constant__ SepW<R> w,
-                                                                            const __grid_constant__ Args2D a)
-{
-    constexpr int TW = 32 * RX;                 // output columns per strip
-    constexpr int PADX = (N + 3) & ~3;          // staged row starts PADX columns left of the strip (16 B aligned)
-    constexpr int DX = PADX - N;
-    constexpr int ROWF = TW + 2 * PADX;         // floats per staged row
-    constexpr int ROWCH = ROWF / 4;             // 16-byte chunks per staged row
-    // static accumulator ring (one column pass per ring phase) vs shifting blocks: the ring needs
-    // (n+1) copies of the column pass, which must stay inside the 32 KB instruction cache
-    // (17x17 rank-4: 2448 FFMA2, measured 9 % slower than the shifting blocks)
-    // (2 columns per lane, half-windows 9-16: the ring measured 9 % slower than the blocks at 25x25)
-    constexpr bool RING = SG2D_RING && N <= 8 && (N + 1) * (2 * N + 1) * R * RX <= SG2D_RING_MAX;
-    constexpr int NA = RING ? 2 * N + 2 : 2 * N + kU;   // output rows in flight per column
-    constexpr int WIN = RX + DX + 2 * N;        // floats of the row window a lane touches
-    constexpr int VW = RX >= 4 ? 4 : 2;         // floats per shared load
-    constexpr int NV = (WIN + VW - 1) / VW;
-
-    __shared__ __align__(16) float s_ring[kWarps][kRing][ROWF];
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float(*ring)[ROWF] = s_ring[warp];
-
-    // 16-byte copies need aligned rows, whole chunks a width that is a multiple of 4; other images take the
-    // out-of-line per-chunk path for every strip
-    const bool simple_rows = ((reinterpret_cast<uintptr_t>(a.in) & 15) | (a.in_stride & 3) | (a.in_image_pitch & 3) | (a.cols & 3)) == 0;
-    const int Ylo = a.cy, Yhi = a.cy + a.out_rows;      // stored region in full-image coordinates
-    const int Xlo = a.cx, Xhi = a.cx + a.out_cols;
-    const int strips = (Xhi + TW - 1) / TW;
-    const int kBand = a.band_rows;
-    const int bands = (a.out_rows + kBand - 1) / kBand;
-    const long long per_img = static_cast<long long>(strips) * bands;
-    const long long items = per_img * a.n_images;
-
-    // Work items are handed out dynamically (one atomic per item): item times differ (edge strips, first /
-    // last bands, L2 hits on shared halo columns); a static round-robin measured 12 % slower on config 4.
-    for (;;) {
-        unsigned ticket = 0;
-        if (lane == 0) ticket = atomicAdd(a.counter, 1u);
-        const long long item = __shfl_sync(0xffffffffu, ticket, 0);
-        if (item >= items) break;
-        // longest first: the items of the two edge strips (extra pad-column copies; much slower on the
-        // out-of-line path of unaligned / ragged images)
-        // are handed out before everything else, so none of them is left for the tail of the launch;
-        // the interior strips follow image by image, band by band, neighbours in x back to back (their
-        // halo columns meet in L2)
-        const int nedge = strips < 2 ? strips : 2;
-        const long long edge_items = static_cast<long long>(nedge) * bands * a.n_images;
-        long long img;
-        int band, strip;
-        if (item < edge_items) {
-            const long long q = item / nedge;
-            strip = (item - q * nedge) ? strips - 1 : 0;
-            img = q / bands;
-            band = static_cast<int>(q - img * bands);
-        } else {
-            const int inner = strips - 2;
-            const long long q = (item - edge_items) / inner;
-            strip = 1 + static_cast<int>((item - edge_items) - q * inner);
-            img = q / bands;
-            band = static_cast<int>(q - img * bands);
-        }
-        const int x0 = strip * TW;
-        if (x0 + TW <= Xlo) continue;                   // strip entirely left of the stored region (VALID)
-        const int Y0 = Ylo + band * kBand;
-        const int nrows = min(kBand, Yhi - Y0);
-        const int steps = nrows + 2 * N;
-        const float* in = a.in + img * a.in_image_pitch;
-        // virtual output base: element (Y, X) of the full-size result lives at vout + Y*os + X
-        float* vout = a.out + img * a.out_image_pitch - static_cast<long long>(a.cy) * a.out_stride - a.cx;
-
-        // ---- staging of input rows ----
-        // Rows t, t+1 (t even) go to ring slots t mod 8 and the next one.  Images with 16-byte aligned
-        // rows and a width that is a multiple of 4 (chunks are then entirely inside or outside the image):
-        //   * chunks inside the image: one or two 16-byte copies per lane and row, predicate fixed per item
-        //     (always true for interior strips); interior bands advance a running source pointer, the
-        //     first / last band maps the row index (clamp / reflect);
-        //   * pad columns of the first / last strip: one element per lane (4-byte copy from the column
-        //     the boundary rule maps it to) -- 2 x 8 elements per step for a 15x15 window.
-        // Everything else (unaligned rows, ragged widths) takes the out-of-line per-chunk path.
-        const int steps2 = (steps + 1) & ~1;   // rows are consumed two per step, see below
-        const bool y_in = (Y0 - N >= 0) && (Y0 - N + steps2 <= a.rows);
-        const int xb = x0 - PADX;                                        // image column of the slot's first float
-        const bool x_in = xb >= 0 && xb + ROWF <= a.cols;                // interior strip: no pad columns
-        bool pch[(ROWCH + 31) / 32];                                     // this lane's chunk(s) lie inside the image
-#pragma unroll
-        for (int c0 = 0; c0 < ROWCH; c0 += 32) {
-            const int xin = xb + 4 * (c0 + lane);
-            pch[c0 / 32] = (c0 + 32 <= ROWCH || lane < ROWCH - c0) && xin >= 0 && xin + 4 <= a.cols;
-        }
-        float* const ring_lane = &ring[0][0] + 4 * lane;
-        const unsigned ring_lane_s = static_cast<unsigned>(__cvta_generic_to_shared(ring_lane));
-        // this lane's first chunk of the NEXT row to stage (interior bands)
-        const float* src_next = in + static_cast<long long>(Y0 - N) * a.in_stride + xb + 4 * lane;
-        const float* const xbase = in + xb + 4 * lane;
-        auto stage_pair = [&](int t) {
-            const int slot = t & (kRing - 1);
-            if (simple_rows) {
-                const float *s0, *s1;
-                if (y_in) {
-                    s0 = src_next;
-                    s1 = s0 + a.in_stride;
-                    src_next = s1 + a.in_stride;
-                } else {
-                    s0 = xbase + static_cast<long long>(map_index(Y0 - N + t, a.rows, a.boundary)) * a.in_stride;
-                    s1 = xbase + static_cast<long long>(map_index(Y0 - N + t + 1, a.rows, a.boundary)) * a.in_stride;
-                }
-                const unsigned d = ring_lane_s + slot * (ROWF * 4);
-                if (x_in) {   // interior strip: nothing to decide per lane
-#pragma unroll
-                    for (int c0 = 0; c0 < ROWCH; c0 += 32)
-                        if (c0 + 32 <= ROWCH || lane < ROWCH - c0) {
-                            cp_async16_s(d + 16 * c0, s0 + 4 * c0);
-                            cp_async16_s(d + ROWF * 4 + 16 * c0, s1 + 4 * c0);
-                        }
-                } else {
-#pragma unroll
-                    for (int c0 = 0; c0 < ROWCH; c0 += 32)
-                        if (pch[c0 / 32]) {
-                            cp_async16_s(d + 16 * c0, s0 + 4 * c0);
-                            cp_async16_s(d + ROWF * 4 + 16 * c0, s1 + 4 * c0);
-                        }
-                    const int nl = xb < 0 ? -xb : 0;                                 // pad elements left of the image
-                    const int nr = xb + ROWF > a.cols ? xb + ROWF - a.cols : 0;      // ... and right of it
-                    stage_pads(d - 16 * lane, s0 - xb - 4 * lane, s1 - xb - 4 * lane, ROWF * 4, nl + nr, nl, xb, a.cols, a.boundary, lane);
-                }
-            } else {
-                stage_edge_pair<ROWCH, ROWF>(ring_lane_s + slot * (ROWF * 4),
-                                             in + static_cast<long long>(map_index(Y0 - N + t, a.rows, a.boundary)) * a.in_stride,
-                                             in + static_cast<long long>(map_index(Y0 - N + t + 1, a.rows, a.boundary)) * a.in_stride,
-                                             xb, a.cols, a.boundary, lane);
-            }
-        };
-        // store side, hoisted: this lane's columns, whether they lie inside the stored region and
-        // whether a vector store is legal; the row pointer advances by the output pitch per emitted row
-        const int X = x0 + RX * lane;
-        float* dst_row = vout + static_cast<long long>(Y0) * a.out_stride + X;
-        constexpr int SV = RX >= 4 ? 4 : 2;  // floats per store instruction
-        const bool st_vec = X >= Xlo && X + RX <= Xhi && (a.out_stride % SV) == 0 &&
-                            (reinterpret_cast<uintptr_t>(dst_row) & (4 * SV - 1)) == 0;
-
-        // Rows are consumed two per step: one wait / sync / loop overhead per two rows, and every
-        // column weight (a uniform register that has to be re-loaded each step, 46 weights do not fit
-        // the uniform register file next to everything else) is used for both rows.  An odd row count
-        // is padded with one extra (boundary-mapped) row whose contributions are never emitted.
-        __syncwarp();  // the previous item's last reads of the ring are done
-#pragma unroll 1
-        for (int t = 0; t < kAhead; t += 2) {
-            if (t < steps2) stage_pair(t);
-            cp_async_commit();
-        }
-
-        // acc[jp][i]: partially accumulated output rows of the column pair (2jp, 2jp+1) of this lane.
-        //   RING:  output row y (band-local, y = t - wy) lives in slot (y mod NA), NA = 2n+2; the main loop
-        //          is unrolled over a full period of the ring (n+1 steps), so every index is static and
-        //          no register ever moves.
-        //   else:  slot i = output row (block base - 2n + i); blocks of kU rows end with a register shift.
-        float2 acc[RX / 2][NA];
-#pragma unroll
-        for (int jp = 0; jp < RX / 2; ++jp)
-#pragma unroll
-            for (int i = 0; i < NA; ++i) acc[jp][i] = make_float2(0.f, 0.f);
-
-        auto row_pass = [&](int t, float2 (&hp)[R][RX / 2]) {
-            float xs[NV * VW];
-            const float* rowp = ring_lane + (t & (kRing - 1)) * ROWF + (RX - 4) * lane;
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                if constexpr (VW == 4) {
-                    const float4 q = *reinterpret_cast<const float4*>(rowp + 4 * v);
-                    xs[4 * v] = q.x; xs[4 * v + 1] = q.y; xs[4 * v + 2] = q.z; xs[4 * v + 3] = q.w;
-                } else {
-                    const float2 q = *reinterpret_cast<const float2*>(rowp + 2 * v);
-                    xs[2 * v] = q.x; xs[2 * v + 1] = q.y;
-                }
-            }
-#pragma unroll
-            for (int jp = 0; jp < RX / 2; ++jp) {
-                const int c0 = 2 * jp + DX + N;
-                const float2 ctr = make_float2(xs[c0], xs[c0 + 1]);
-#pragma unroll
-                for (int r = 0; r < R; ++r) hp[r][jp] = __fmul2_rn(make_float2(w.rc[r], w.rc[r]), ctr);
-            }
-#pragma unroll
-            for (int k = 1; k <= N; ++k)
-#pragma unroll
-                for (int jp = 0; jp < RX / 2; ++jp) {
-                    const int c0 = 2 * jp + DX + N;
-                    const float2 sk = make_float2(fmaf(w.sx, xs[c0 - k], xs[c0 + k]),      // +/-1 multiply is exact
-                                                  fmaf(w.sx, xs[c0 + 1 - k], xs[c0 + 1 + k]));
-#pragma unroll
-                    for (int r = 0; r < R; ++r)
-                        hp[r][jp] = __ffma2_rn(make_float2(w.rk[r][k - 1], w.rk[r][k - 1]), sk, hp[r][jp]);
-                }
-        };
-        auto emit = [&](const float2 (&v)[RX / 2]) {
-            if (st_vec) {
-                if constexpr (RX >= 4) {
-#pragma unroll
-                    for (int q = 0; q < RX / 4; ++q)
-                        sg::st_cs_f4(dst_row + 4 * q, make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y));
-                } else {
-                    *reinterpret_cast<float2*>(dst_row) = v[0];
-                }
-            } else {
-                emit_ragged<RX>(dst_row, v, X, Xlo, Xhi);
-            }
-            dst_row += a.out_stride;
-        };
-
-        if constexpr (RING) {
-            // The loop over steps stays rolled (one copy of the staging and row-pass code); only the column
-            // pass exists once per phase of the ring, selected by a switch.  A fully unrolled period
-            // (n+1 steps) measured 59 KB of loop body: more than the 32 KB instruction cache, the warps
-            // of an SM are spread over the whole body and stall on instruction fetch.
-            int phase = 0;
-#pragma unroll 1
-            for (int t = 0; t < steps2; t += 2) {
-                cp_async_wait<kAhead / 2 - 1>();   // rows t and t+1 have landed (this lane's part) ...
-                __syncwarp();                      // ... and everybody else's; rows t-2, t-1 are fully consumed
-                if (t + kAhead < steps2) stage_pair(t + kAhead);   // into the slots of rows t-2, t-1
-                cp_async_commit();
-
-                float2 h0[R][RX / 2], h1[R][RX / 2];
-                row_pass(t, h0);
-                row_pass(t + 1, h1);
-
-                float2 v0[RX / 2], v1[RX / 2];
-                static_switch<NA / 2>(phase, [&](auto sc) {
-                    constexpr int s2 = 2 * decltype(sc)::value;   // ring position of row t
-                    // column pass: row t is window row wy of output row t - wy -> slot (s2 - wy) mod NA, row
-                    // t+1 of the slot after it.  wy = 0 opens a new output row (plain product: the slot
-                    // still holds the row stored 2n+2 rows ago).
-#pragma unroll
-                    for (int wy = 0; wy <= 2 * N; ++wy)
-#pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            const float cw = w.col[r][wy];
-                            constexpr int kOff = 4 * NA;   // keeps the modulo argument positive
-                            const int i0 = (s2 - wy + kOff) % NA, i1 = (s2 + 1 - wy + kOff) % NA;
-#pragma unroll
-                            for (int jp = 0; jp < RX / 2; ++jp) {
-                                if (wy == 0 && r == 0) {
-                                    acc[jp][i0] = __fmul2_rn(make_float2(cw, cw), h0[r][jp]);
-                                    acc[jp][i1] = __fmul2_rn(make_float2(cw, cw), h1[r][jp]);
-                                } else {
-                                    acc[jp][i0] = __ffma2_rn(make_float2(cw, cw), h0[r][jp], acc[jp][i0]);
-                                    acc[jp][i1] = __ffma2_rn(make_float2(cw, cw), h1[r][jp], acc[jp][i1]);
-                                }
-                            }
-                        }
-                    // output rows t - 2n and t + 1 - 2n are complete (their slots are dead until wy = 0 re-opens
-                    // them, so these copies fold into the last FFMA2 of each row)
-#pragma unroll
-                    for (int jp = 0; jp < RX / 2; ++jp) {
-                        v0[jp] = acc[jp][(s2 + 2) % NA];
-                        v1[jp] = acc[jp][(s2 + 3) % NA];
-                    }
-                });
-                phase = phase + 1 == NA / 2 ? 0 : phase + 1;
-                if (t >= 2 * N && t - 2 * N < nrows) emit(v0);
-                if (t + 1 >= 2 * N && t + 1 - 2 * N < nrows) emit(v1);
-            }
-        } else {
-#pragma unroll 1
-            for (int tb = 0; tb * kU < steps2; ++tb) {
-#pragma unroll
-                for (int u = 0; u < kU; u += 2) {
-                    const int t = tb * kU + u;
-                    if (t < steps2) {
-                        cp_async_wait<kAhead / 2 - 1>();   // rows t and t+1 have landed (this lane's part) ...
-                        __syncwarp();                      // ... and everybody else's; rows t-2, t-1 are fully consumed
-                        if (t + kAhead < steps2) stage_pair(t + kAhead);   // into the slots of rows t-2, t-1
-                        cp_async_commit();
-
-                        float2 h0[R][RX / 2], h1[R][RX / 2];
-                        row_pass(t, h0);
-                        row_pass(t + 1, h1);
-
-                        // ---- column pass: scatter both rows into the output rows in flight ----
-                        // row t is window row wy of output i = u + 2n - wy; row t+1 is window row wy of output i+1
-#pragma unroll
-                        for (int wy = 0; wy <= 2 * N; ++wy)
-#pragma unroll
-                            for (int r = 0; r < R; ++r) {
-                                const float cw = w.col[r][wy];
-                                const int i = u + 2 * N - wy;
-#pragma unroll
-                                for (int jp = 0; jp < RX / 2; ++jp) {
-                                    acc[jp][i] = __ffma2_rn(make_float2(cw, cw), h0[r][jp], acc[jp][i]);
-                                    acc[jp][i + 1] = __ffma2_rn(make_float2(cw, cw), h1[r][jp], acc[jp][i + 1]);
-                                }
-                            }
-
-                        // ---- output rows u and u+1 of the block are complete ----
-                        if (t >= 2 * N && t - 2 * N < nrows) {
-                            float2 v[RX / 2];
-#pragma unroll
-                            for (int jp = 0; jp < RX / 2; ++jp) v[jp] = acc[jp][u];
-                            emit(v);
-                        }
-                        if (t + 1 >= 2 * N && t + 1 - 2 * N < nrows) {
-                            float2 v[RX / 2];
-#pragma unroll
-                            for (int jp = 0; jp < RX / 2; ++jp) v[jp] = acc[jp][u + 1];
-                            emit(v);
-                        }
-                    }
-                }
-                // block done: drop the kU completed rows
-#pragma unroll
-                for (int jp = 0; jp < RX / 2; ++jp)
-#pragma unroll
-                    for (int i = 0; i < NA; ++i) acc[jp][i] = (i + kU < NA) ? acc[jp][i + kU] : make_float2(0.f, 0.f);
-            }
-        }
-        cp_async_wait<0>();
-    }
-}
-
-// Ticket counter of one launch: 4 bytes from the device's stream-ordered pool, zeroed before and freed
-// after the kernel in stream order -- private to the launch whatever other streams, threads or captured
-// graphs are doing.  The pool keeps its memory (release threshold raised once per device), so the
-// alloc / free pair costs about a microsecond of host time.
-cudaError_t acquire_counter(cudaStream_t stream, unsigned** out)
-{
-    static std::mutex mu;
-    static bool pool_ready[64] = {};
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < 64) {
-        std::lock_guard<std::mutex> lk(mu);
-        if (!pool_ready[dev]) {
-            cudaMemPool_t pool;
-            e = cudaDeviceGetDefaultMemPool(&pool, dev);
-            if (e != cudaSuccess) return e;
-            unsigned long long keep = ~0ull;
-            e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-            if (e != cudaSuccess) return e;
-            pool_ready[dev] = true;
-        }
-    }
-    e = cudaMallocAsync(reinterpret_cast<void**>(out), sizeof(unsigned), stream);
-    if (e != cudaSuccess) return e;
-    return cudaMemsetAsync(*out, 0, sizeof(unsigned), stream);
-}
-
-template <int N, int R>
-cudaError_t launch_nr(const Args2D& a, const SepPlan& plan, cudaStream_t stream)
-{
-    constexpr int RX = (N <= 8 && SG2D_RX4) ? SG2D_RXW : 2;
-    SepW<R> w;
-    const float sc = a.scale;
-    for (int r = 0; r < R; ++r) {
-        // N = max(nx, ny): the shorter factor is centred and zero-padded (the extra taps multiply
-        // boundary-mapped, i.e. finite, samples by 0)
-        w.rc[r] = plan.row[r][plan.nx];
-        for (int k = 1; k <= N; ++k) w.rk[r][k - 1] = k <= plan.nx ? plan.row[r][plan.nx + k] : 0.0f;
-        for (int k = 0; k <= 2 * N; ++k) {
-            const int j = k - N + plan.ny;
-            w.col[r][k] = (j >= 0 && j <= 2 * plan.ny) ? plan.col[r][j] * sc : 0.0f;
-        }
-    }
-    w.sx = plan.parity_x < 0 ? -1.0f : 1.0f;
-    auto kern = sep_kernel<N, R, RX>;
-    // resident CTAs per SM / SM count of this instantiation (same on every B200; filled once, any thread)
-    static std::atomic<int> s_bps{0}, s_sms{0};
-    int bps = s_bps.load(std::memory_order_acquire), sms = s_sms.load(std::memory_order_acquire);
-    if (bps == 0 || sms == 0) {
-        int dev = 0, nb = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kWarps * 32, 0);
-        if (e != cudaSuccess) return e;
-        bps = nb > 0 ? nb : 1;
-        s_sms.store(sms, std::memory_order_release);
-        s_bps.store(bps, std::memory_order_release);
-    }
-    constexpr int TW = 32 * RX;
-    const long long strips = (a.cx + a.out_cols + TW - 1) / TW;
-    // band height: as tall as possible (2n warm-up rows per band are recomputed), but short enough that
-    // the launch has >= 4 work items per resident warp
-    Args2D aa = a;
-    const long long want = 4LL * sms * bps * kWarps;
-    long long nb = (want + strips * a.n_images - 1) / (strips * a.n_images);   // bands per image wanted
-    long long band = (a.out_rows + nb - 1) / (nb > 0 ? nb : 1);
-    band = (band + kU - 1) / kU * kU;
-    if (band < 8 * N + 8) band = 8 * N + 8;   // keep the warm-up overhead <= 25 %
-    if (band > kBandMax) band = kBandMax;
-    aa.band_rows = static_cast<int>(band);
-    const long long bands = (a.out_rows + band - 1) / band;
-    const long long items = strips * bands * a.n_images;
-    if (items <= 0) return cudaSuccess;
-    if (items >= (1LL << 31)) return cudaErrorInvalidValue;
-    cudaError_t ec = acquire_counter(stream, &aa.counter);
-    if (ec != cudaSuccess) return ec;
-    long long grid = static_cast<long long>(sms) * bps;
-    const long long need = (items + kWarps - 1) / kWarps;
-    if (grid > need) grid = need;
-    kern<<<static_cast<unsigned>(grid), kWarps * 32, 0, stream>>>(w, aa);
-    sg::g_launches.fetch_add(1);
-    ec = cudaGetLastError();
-    const cudaError_t ef = cudaFreeAsync(aa.counter, stream);
-    return ec != cudaSuccess ? ec : ef;
-}
-
 template <int N>
 cudaError_t launch_n(const Args2D& a, const SepPlan& plan, cudaStream_t stream)
 {
     switch (plan.rank) {
-        case 1: return launch_nr<N, 1>(a, plan, stream);
-        case 2: return launch_nr<N, 2>(a, plan, stream);
-        case 3: return launch_nr<N, 3>(a, plan, stream);
-        case 4: return launch_nr<N, 4>(a, plan, stream);
+        case 1: return launch_nr<N, 1, false>(a, plan, stream);
+        case 2: return launch_nr<N, 2, false>(a, plan, stream);
+        case 3: return launch_nr<N, 3, false>(a, plan, stream);
+        case 4: return launch_nr<N, 4, false>(a, plan, stream);
         default: return cudaErrorInvalidValue;
     }
 }
 
+// Ticket counter of one launch: 4 bytes from a PRIVATE stream-ordered pool of the device (created on first
+// use; the application's default pool and its release threshold are left alone), zeroed before and freed
+// after the kernel in stream order -- private to the launch whatever other streams, threads or captured
+// graphs are doing.  The pool keeps its memory, so the alloc / free pair costs about a microsecond of host time.
+std::mutex g_pool_mu;
+cudaMemPool_t g_pool[64] = {};
+
 }  // namespace
+
+cudaError_t acquire_counter(cudaStream_t stream, unsigned** out)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    cudaMemPool_t pool;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (!g_pool[dev]) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            e = cudaMemPoolCreate(&g_pool[dev], &props);
+            if (e != cudaSuccess) return e;
+            unsigned long long keep = ~0ull;
+            e = cudaMemPoolSetAttribute(g_pool[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+            if (e != cudaSuccess) return e;
+        }
+        pool = g_pool[dev];
+    }
+    e = cudaMallocFromPoolAsync(reinterpret_cast<void**>(out), sizeof(unsigned), pool, stream);
+    if (e != cudaSuccess) return e;
+    return cudaMemsetAsync(*out, 0, sizeof(unsigned), stream);
+}
 
 // The streaming kernel is instantiated per half-window N = max(nx, ny) (a rectangular window runs with
 // its shorter factor zero-padded).  Half-windows above 16 and the exact flavour run through sg2d_direct.cu.
@@ -604,6 +66,7 @@ bool separable_supported(const Args2D& a, const SepPlan& plan)
 
 cudaError_t launch_separable(const Args2D& a, const SepPlan& plan, cudaStream_t stream)
 {
+    if (plan.additive) return launch_additive(a, plan, stream);
     switch (plan.nx > plan.ny ? plan.nx : plan.ny) {
 #define SG2D_CASE(n) case n: return launch_n<n>(a, plan, stream);
         SG2D_CASE(1) SG2D_CASE(2) SG2D_CASE(3) SG2D_CASE(4) SG2D_CASE(5) SG2D_CASE(6) SG2D_CASE(7) SG2D_CASE(8)

@@ -60,6 +60,7 @@ struct Args1D {
     int edge_lead, edge_trail;  // 1: outputs [0,n) / [len-n,len) come from the polynomial edge table
     long long tiles_per_row, ntiles;  // segments (1024 outputs) per row / in the launch; ntiles < 2^31
     int pack_g;              // short-row kernel (sg1d_packed.cuh): lanes per row (16, 8, 4); ntiles = row groups
+    int out_tma;             // TMA kernel (sg1d_tma.cuh): full segments are stored by one bulk-tensor copy
 };
 
 // ---------------------------------------------------------------------------------------------

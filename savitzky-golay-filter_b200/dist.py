@@ -144,13 +144,24 @@ def exchange_halo_rows(band, ny: int, group=None):
     return top, bottom
 
 
-def apply_image_bands(filt, band, boundary="constant", out=None, group=None):
+def apply_image_bands(filt, band, boundary="constant", out=None, group=None, row_begin=None):
     """Filters this rank's horizontal band of ONE image sharded by rows over the group: halo rows from the
-    ring neighbours, then savgol2d_apply_band.  The result equals the same rows of the whole-image filter."""
+    ring neighbours, then savgol2d_apply_band_at.  The result equals the same rows of the whole-image filter,
+    bit for bit.  ``row_begin`` = image row of band[0] (default: the sum of the lower ranks' band heights)."""
     import torch
+    import torch.distributed as dist
 
     ny = int(filt.config.half_window_y)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if row_begin is None:
+        row_begin = 0
+        if world > 1:
+            heights = [None] * world
+            dist.all_gather_object(heights, int(band.shape[0]), group=group)
+            row_begin = sum(heights[:rank])
     top, bottom = exchange_halo_rows(band, ny, group)
     parts = ([top] if top is not None else []) + [band] + ([bottom] if bottom is not None else [])
     buf = torch.cat(parts).contiguous() if len(parts) > 1 else band
-    return filt.apply_band(buf, ny if top is not None else 0, ny if bottom is not None else 0, boundary, out=out)
+    t = ny if top is not None else 0
+    return filt.apply_band(buf, t, ny if bottom is not None else 0, boundary, out=out, image_row0=row_begin - t)

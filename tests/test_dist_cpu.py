@@ -95,7 +95,8 @@ class _OracleBandFilter:
             half_window_y = ny
         self.config = _Cfg()
 
-    def apply_band(self, buf, top, bottom, boundary, out=None):
+    def apply_band(self, buf, top, bottom, boundary, out=None, image_row0=0):
+        self.row0_seen = image_row0
         full = self.o.apply(buf.numpy().copy(), boundary)
         return torch.from_numpy(full[top: full.shape[0] - bottom].copy())
 
@@ -113,6 +114,7 @@ def _band_worker(rank, world, port, boundary, q):
     y = sgd.apply_image_bands(f, torch.from_numpy(img[a:b].copy()), boundary).numpy()
     ref = O.Filter2D(nx, ny, order).apply(img, boundary)[a:b]
     ok = y.shape == ref.shape and np.array_equal(y.view(np.uint32), ref.view(np.uint32))
+    ok = ok and f.row0_seen == a - (ny if rank > 0 else 0)   # the band's position in the image reaches the kernel
     t = torch.tensor([1 if ok else 0])
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -197,7 +197,7 @@ def test_row_bands_reassemble_whole_image(oracle, boundary):
             for lo, hi in zip(cuts[:-1], cuts[1:]):
                 top = ny if lo > 0 else 0
                 bottom = ny if hi < 700 else 0
-                f.apply_band(img[lo - top: hi + bottom], top, bottom, boundary, out=out[lo:hi])
+                f.apply_band(img[lo - top: hi + bottom], top, bottom, boundary, out=out[lo:hi], image_row0=lo - top)
             sg.set_exact(False)
             assert torch.equal(out, whole), (nx, ny, order, exact, boundary)
         f.close()
