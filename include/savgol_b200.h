@@ -238,12 +238,14 @@ unsigned long long savgol_b200_launch_count(void);
 /* ... of which launches of the bulk-tensor (TMA) 1D kernels (contiguous 16-byte aligned rows of >= 1024
  * samples, default arithmetic); SAVGOL_B200_NO_TMA=1 in the environment routes them to the cp.async kernels. */
 unsigned long long savgol_b200_tma_launch_count(void);
-/* Experiment / test switch for the above (process-wide; default on). */
-void savgol_b200_set_tma(int on);
+/* Experiment / test switch for the above (process-wide): 0 never, 1 (default) where they measured faster
+ * (half-windows up to 19, launches of >= 2048 segments), 2 wherever the data layout allows. */
+void savgol_b200_set_tma(int how);
 /* Arithmetic flavour: 0 (default) = FMA chains, within 1e-6*max|x|/dt^d of the
  * reference; 1 = "exact": the reference's own summation order with unfused
  * multiply/add, bit-identical to the reference C code (slower; for verification). */
-void savgol_b200_set_exact(int exact);
+void savgol_b200_set_exact(int exact);          /* the calling host thread's flavour */
+void savgol_b200_set_exact_default(int exact);  /* process default, for threads that never chose */
 int savgol_b200_get_exact(void);
 
 /* 1D batch ---------------------------------------------------------------- */
@@ -266,6 +268,36 @@ int savgol_apply_halo(const SavgolFilter *filter, const float *input, float *out
                       const float *left_halo, const float *right_halo);
 
 /* Peer memory for the partitioned signal (one process per GPU) -------------- */
+
+/* Multi-GPU from one process ---------------------------------------------- */
+
+/* SURVEY.md 8b rule (4) / 8e: the reference's user is a C caller looping over savgol_apply
+ * (ref: include/iterative/savgolFilter.h:16-19, 130-203); these calls hand that caller every GPU of the
+ * box without a process group.
+ *
+ * savgol_apply_batch_multi: HOST buffers.  `devices[0..n_devices)` are CUDA device ordinals.  With at least
+ * as many signals as devices the signals are sharded in contiguous blocks (no communication); otherwise
+ * (one very long signal) every signal is partitioned along its length and each slice is staged with its
+ * n-sample halos from the host signal.  One staging pipeline per device, all running concurrently.
+ * Result and return codes are those of savgol_apply_batch. */
+int savgol_apply_batch_multi(const SavgolFilter *filter, const float *input, float *output,
+                             size_t n_signals, size_t length, size_t in_pitch, size_t out_pitch,
+                             const int *devices, int n_devices);
+
+/* savgol_apply_slices: one signal that already lives on several GPUs as consecutive slices, slice i =
+ * in_slices[i][0..lengths[i]) in the memory of devices[i] (the same device may appear more than once).
+ * Peer access is enabled between ring neighbours and each device's kernel reads its 2 x half_window halo
+ * samples directly from the neighbour's memory over NVLink -- no copy, no collective, one launch per device.
+ * PERIODIC wraps from the last slice to the first; the other modes treat the outer ends as signal ends.
+ * The inputs must be complete before the call; it returns when every output slice is complete.  0 / -1. */
+int savgol_apply_slices(const SavgolFilter *filter, const float *const *in_slices, float *const *out_slices,
+                        const size_t *lengths, const int *devices, int n_slices);
+
+/* Device memory for callers without CUDA headers (examples/c_multi_gpu.c). */
+int savgol_b200_device_count(void);
+void *savgol_b200_alloc(int device, size_t bytes);
+void savgol_b200_free(int device, void *ptr);
+int savgol_b200_copy(void *dst, const void *src, size_t bytes);   /* any direction, synchronous; 0 / -1 */
 
 /* The halo pointers of savgol_apply_halo() may point into ANOTHER GPU's memory: the kernel
  * reads the 2n halo samples over NVLink while it stages the slice, so the "halo exchange"

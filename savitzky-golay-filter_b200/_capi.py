@@ -94,7 +94,15 @@ PROTOTYPES = {
     "savgol_b200_tma_launch_count": (C.c_ulonglong, []),
     "savgol_b200_set_tma": (None, [C.c_int]),
     "savgol_b200_set_exact": (None, [C.c_int]),
+    "savgol_b200_set_exact_default": (None, [C.c_int]),
     "savgol_b200_get_exact": (C.c_int, []),
+    "savgol_apply_batch_multi": (C.c_int, [FP, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t,
+                                           C.POINTER(C.c_int), C.c_int]),
+    "savgol_apply_slices": (C.c_int, [FP, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.c_int]),
+    "savgol_b200_device_count": (C.c_int, []),
+    "savgol_b200_alloc": (C.c_void_p, [C.c_int, C.c_size_t]),
+    "savgol_b200_free": (None, [C.c_int, C.c_void_p]),
+    "savgol_b200_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "savgol_apply_batch": (C.c_int, [FP, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t]),
     "savgol_apply_halo": (C.c_int, [FP, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "savgol2d_apply_batch": (C.c_int, [F2, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int,

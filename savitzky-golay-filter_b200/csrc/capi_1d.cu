@@ -29,120 +29,13 @@ int mode_of(const SavgolFilter* f)
     }
 }
 
-static size_t chunk_floats()
-{
-    // samples per staged chunk: small enough that pipeline fill + drain (one chunk each way) is a few
-    // percent of a large transfer, large enough to stay near PCIe peak.  Env override for experiments.
-    static size_t v = [] {
-        const char* e = getenv("SAVGOL_B200_CHUNK_MIB");
-        size_t mib = e ? static_cast<size_t>(atoi(e)) : 64;  // measured on B200: 64 MiB 23.0 ms/GiB-step, 16 MiB 23.2, 4 MiB 26.9
-        if (mib < 1) mib = 1;
-        return mib << 18;
-    }();
-    return v;
-}
-#define kChunkFloats chunk_floats()
-
-// Batch of contiguous-sample rows living in HOST memory (in and out both host).
-// Rows short enough are grouped into chunks of whole rows; a row longer than a chunk is cut
-// along its length and every piece carries explicit n-sample halos.
-bool run1d_host(const SavgolFilter* f, const float* in, float* out, size_t rows, size_t len,
-                size_t in_pitch, size_t out_pitch, int mode, bool poly_edges, int arith)
-{
-    std::lock_guard<std::mutex> lk(sge::g_pipe_mu);
-    const int n = f->config.half_window;
-    const size_t padl = static_cast<size_t>((n + 3) & ~3);
-    sge::Pipeline& P = sge::g_pipe;
-
-    if (len <= kChunkFloats) {
-        // ---- chunks of whole rows ----
-        const size_t rows_per = std::max<size_t>(1, std::min(rows, kChunkFloats / len));
-        if (!P.ensure(rows_per * len, rows_per * len)) return false;
-        size_t done = 0;
-        for (size_t c = 0; done < rows; ++c, done += rows_per) {
-            const int s = static_cast<int>(c % sge::Pipeline::kSlots);
-            const size_t nr = std::min(rows_per, rows - done);
-            if (c >= sge::Pipeline::kSlots) {
-                // slot reuse: its previous D2H must have drained before we overwrite d_out/d_in
-                if (!cuda_ok(cudaStreamWaitEvent(P.s_in, P.e_out[s], 0), "wait")) return false;
-            }
-            if (!cuda_ok(cudaMemcpy2DAsync(P.d_in[s], len * sizeof(float), in + done * in_pitch, in_pitch * sizeof(float),
-                                           len * sizeof(float), nr, cudaMemcpyHostToDevice, P.s_in), "H2D")) return false;
-            cudaEventRecord(P.e_in[s], P.s_in);
-            cudaStreamWaitEvent(P.s_k, P.e_in[s], 0);
-            if (c >= sge::Pipeline::kSlots) cudaStreamWaitEvent(P.s_k, P.e_out[s], 0);
-            sge::Problem1D p{};
-            p.filter = f; p.in = P.d_in[s]; p.out = P.d_out[s];
-            p.rows = nr; p.len = len;
-            p.in_row_bytes = p.out_row_bytes = len * sizeof(float);
-            p.in_stride = p.out_stride = 4;
-            p.mode = mode; p.edge_lead = p.edge_trail = poly_edges; p.arith = arith;
-            if (!sge::run1d_device(p, P.s_k)) return false;
-            cudaEventRecord(P.e_k[s], P.s_k);
-            cudaStreamWaitEvent(P.s_out, P.e_k[s], 0);
-            if (!cuda_ok(cudaMemcpy2DAsync(out + done * out_pitch, out_pitch * sizeof(float), P.d_out[s], len * sizeof(float),
-                                           len * sizeof(float), nr, cudaMemcpyDeviceToHost, P.s_out), "D2H")) return false;
-            cudaEventRecord(P.e_out[s], P.s_out);
-        }
-        return cuda_ok(cudaStreamSynchronize(P.s_out), "sync") && cuda_ok(cudaStreamSynchronize(P.s_k), "sync");
-    }
-
-    // ---- long rows: pieces of kChunkFloats samples with explicit halos ----
-    // slot layout: [padl-n slack | n left halo | piece | n right halo]
-    const size_t piece = kChunkFloats;
-    if (!P.ensure(padl + piece + 2 * sg::kMaxWs + n, piece + sg::kMaxWs)) return false;
-    size_t c = 0;
-    for (size_t r = 0; r < rows; ++r) {
-        const float* x = in + r * in_pitch;
-        float* y = out + r * out_pitch;
-        for (size_t s0 = 0; s0 < len; ++c) {
-            size_t s1 = std::min(len, s0 + piece);
-            if (len - s1 < static_cast<size_t>(2 * n + 1)) s1 = len;  // keep the last piece >= one window
-            const size_t plen = s1 - s0;
-            const int s = static_cast<int>(c % sge::Pipeline::kSlots);
-            if (c >= sge::Pipeline::kSlots && !cuda_ok(cudaStreamWaitEvent(P.s_in, P.e_out[s], 0), "wait")) return false;
-            float* base = P.d_in[s];
-            float* dx = base + padl;
-            const bool has_l = s0 > 0, has_r = s1 < len;
-            // body plus whatever neighbouring samples exist, in one copy
-            const size_t c0 = has_l ? s0 - n : s0, c1 = has_r ? s1 + n : s1;
-            if (!cuda_ok(cudaMemcpyAsync(dx - (s0 - c0), x + c0, (c1 - c0) * sizeof(float), cudaMemcpyHostToDevice, P.s_in), "H2D")) return false;
-            const float* lh = has_l ? dx - n : nullptr;
-            const float* rh = has_r ? dx + plen : nullptr;
-            if (mode == sg::MODE_PERIODIC && !(s0 == 0 && s1 == len)) {
-                // true ends of a periodic signal wrap around: fetch the far end as an explicit halo
-                if (!has_l) { cudaMemcpyAsync(dx - n, x + (len - n), n * sizeof(float), cudaMemcpyHostToDevice, P.s_in); lh = dx - n; }
-                if (!has_r) { cudaMemcpyAsync(dx + plen, x, n * sizeof(float), cudaMemcpyHostToDevice, P.s_in); rh = dx + plen; }
-            }
-            cudaEventRecord(P.e_in[s], P.s_in);
-            cudaStreamWaitEvent(P.s_k, P.e_in[s], 0);
-            if (c >= sge::Pipeline::kSlots) cudaStreamWaitEvent(P.s_k, P.e_out[s], 0);
-            sge::Problem1D p{};
-            p.filter = f; p.in = dx; p.out = P.d_out[s];
-            p.rows = 1; p.len = plen;
-            p.in_row_bytes = p.out_row_bytes = plen * sizeof(float);
-            p.in_stride = p.out_stride = 4;
-            p.lhalo = lh; p.rhalo = rh;
-            p.mode = mode;
-            p.edge_lead = poly_edges && !has_l; p.edge_trail = poly_edges && !has_r;
-            p.arith = arith;
-            if (!sge::run1d_device(p, P.s_k)) return false;
-            cudaEventRecord(P.e_k[s], P.s_k);
-            cudaStreamWaitEvent(P.s_out, P.e_k[s], 0);
-            if (!cuda_ok(cudaMemcpyAsync(y + s0, P.d_out[s], plen * sizeof(float), cudaMemcpyDeviceToHost, P.s_out), "D2H")) return false;
-            cudaEventRecord(P.e_out[s], P.s_out);
-            s0 = s1;
-        }
-    }
-    return cuda_ok(cudaStreamSynchronize(P.s_out), "sync") && cuda_ok(cudaStreamSynchronize(P.s_k), "sync");
-}
-
 // Dispatch on where the caller's buffers live.
 bool run1d_any(const SavgolFilter* f, const float* in, float* out, size_t rows, size_t len,
                size_t in_pitch, size_t out_pitch, int mode, bool poly_edges)
 {
-    if (!sge::device_ready(true)) return false;
     const MemKind ki = sge::classify(in), ko = sge::classify(out);
+    sge::DeviceGuard guard(in);   // device buffers: run on the device that owns them, whatever is current
+    if (!sge::device_ready(true)) return false;
     const int arith = arith_for_batch();
     if (ki == MemKind::Device && ko == MemKind::Device) {
         sge::Problem1D p{};
@@ -170,7 +63,7 @@ bool run1d_any(const SavgolFilter* f, const float* in, float* out, size_t rows, 
             }
             (void)cudaGetLastError();
         }
-        return run1d_host(f, in, out, rows, len, in_pitch, out_pitch, mode, poly_edges, arith);
+        return sge::run1d_host(f, in, out, rows, len, in_pitch, out_pitch, mode, poly_edges, arith);
     }
     fprintf(stderr, "savgol_b200: input and output must both be device pointers or both be host pointers\n");
     return false;
@@ -254,10 +147,11 @@ size_t savgol_apply_valid(const SavgolFilter* filter, const float* input, size_t
 {
     if (filter == nullptr || input == nullptr || output == nullptr) return 0;
     if (input_length < static_cast<size_t>(filter->window_size)) return 0;
-    if (!sge::device_ready(true)) return 0;
     const size_t n = filter->config.half_window;
     const size_t out_len = input_length - 2 * n;
     const MemKind ki = sge::classify(input), ko = sge::classify(output);
+    sge::DeviceGuard guard(input);
+    if (!sge::device_ready(true)) return 0;
     const int arith = arith_for_batch();
     if (ki == MemKind::Device && ko == MemKind::Device) {
         // VALID == the batch stencil on x+n with the first/last n samples as explicit halos
@@ -273,26 +167,10 @@ size_t savgol_apply_valid(const SavgolFilter* filter, const float* input, size_t
         fprintf(stderr, "savgol_b200: input and output must both be device pointers or both be host pointers\n");
         return 0;
     }
-    // host: stage the whole signal, run VALID on the device copy, bring L-2n samples back
-    cudaStream_t st = sge::current_stream();
-    float *din = nullptr, *dout = nullptr;
-    bool ok = cuda_ok(cudaMallocAsync(&din, input_length * sizeof(float), st), "cudaMallocAsync") &&
-              cuda_ok(cudaMallocAsync(&dout, out_len * sizeof(float), st), "cudaMallocAsync");
-    if (ok) ok = cuda_ok(cudaMemcpyAsync(din, input, input_length * sizeof(float), cudaMemcpyHostToDevice, st), "H2D");
-    if (ok) {
-        sge::Problem1D p{};
-        p.filter = filter; p.in = din + n; p.out = dout; p.rows = 1; p.len = out_len;
-        p.in_row_bytes = p.out_row_bytes = out_len * sizeof(float);
-        p.in_stride = p.out_stride = 4;
-        p.lhalo = din; p.rhalo = din + (input_length - n);
-        p.mode = sg::MODE_POLY; p.arith = arith;
-        ok = sge::run1d_device(p, st);
-    }
-    if (ok) ok = cuda_ok(cudaMemcpyAsync(output, dout, out_len * sizeof(float), cudaMemcpyDeviceToHost, st), "D2H");
-    if (ok) ok = cuda_ok(cudaStreamSynchronize(st), "sync");
-    if (din) cudaFreeAsync(din, st);
-    if (dout) cudaFreeAsync(dout, st);
-    return ok ? out_len : 0;
+    // host: outputs [n, L-n) of the signal through the staging pipeline (every piece has real halos)
+    sge::PipeLease lease;
+    if (!lease.ok()) return 0;
+    return sge::run1d_host_range(*lease, filter, input, input_length, n, input_length - n, output, sg::MODE_POLY, false, arith) ? out_len : 0;
 }
 
 int savgol_apply_strided(const SavgolFilter* filter, const void* input, size_t in_stride, size_t in_offset,
@@ -300,8 +178,9 @@ int savgol_apply_strided(const SavgolFilter* filter, const void* input, size_t i
 {
     if (filter == nullptr || input == nullptr || output == nullptr) return -1;  // ref: :882-884 (silent)
     if (count < static_cast<size_t>(filter->window_size)) return -1;
-    if (!sge::device_ready(true)) return -1;
     const MemKind ki = sge::classify(input), ko = sge::classify(output);
+    sge::DeviceGuard guard(input);
+    if (!sge::device_ready(true)) return -1;
     const int arith = arith_for_batch();
     const char* ib = static_cast<const char*>(input) + in_offset;
     char* ob = static_cast<char*>(output) + out_offset;
@@ -363,6 +242,7 @@ int savgol_apply_halo(const SavgolFilter* filter, const float* input, float* out
         fprintf(stderr, "savgol_apply_halo: a periodic slice needs both halos (or none)\n");
         return -1;
     }
+    sge::DeviceGuard guard(input);
     if (!sge::device_ready(true)) return -1;
     if (sge::classify(input) != MemKind::Device || sge::classify(output) != MemKind::Device ||
         (left_halo && sge::classify(left_halo) != MemKind::Device) ||

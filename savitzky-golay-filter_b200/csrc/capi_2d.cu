@@ -109,6 +109,7 @@ bool ranges_overlap2d(const float* a, size_t an, const float* b, size_t bn) { re
 int apply2d_any(const Savgol2DFilter* f, const float* in, int rows, int cols, int is, size_t ipitch,
                 float* out, int os, size_t opitch, size_t n_images, int boundary)
 {
+    sge::DeviceGuard guard(in);
     if (!sge::device_ready(true)) return -1;
     const int nx = f->config.half_window_x, ny = f->config.half_window_y;
     const int orows = boundary == sg2d::B_VALID ? rows - 2 * ny : rows;
@@ -140,8 +141,20 @@ int apply2d_any(const Savgol2DFilter* f, const float* in, int rows, int cols, in
         return -1;
     }
     // host images: one image per pipeline slot, H2D / kernel / D2H overlapped across images
-    std::lock_guard<std::mutex> lk(sge::g_pipe_mu);
-    sge::Pipeline& P = sge::g_pipe;
+    sge::PipeLease lease;
+    if (!lease.ok()) return -1;
+    sge::Pipeline& P = *lease;
+    // in place / overlapping host images: image i's D2H may run while image i+1's H2D is still reading -- stage the
+    // input of overlapping calls from a copy (images that coincide exactly are safe: one image per slot)
+    std::vector<float> aside;
+    {
+        const size_t in_span = (n_images - 1) * ipitch + static_cast<size_t>(rows - 1) * is + cols;
+        const size_t out_span = (n_images - 1) * opitch + static_cast<size_t>(orows - 1) * os + ocols;
+        if (ranges_overlap2d(in, in_span, out, out_span) && !(in == out && is == os && ipitch == opitch && boundary != sg2d::B_VALID)) {
+            aside.assign(in, in + in_span);
+            in = aside.data();
+        }
+    }
     const size_t img_in = static_cast<size_t>(rows) * cols, img_out = static_cast<size_t>(orows) * ocols;
     if (!P.ensure(img_in, img_out)) return -1;
     for (size_t i = 0; i < n_images; ++i) {
@@ -161,7 +174,8 @@ int apply2d_any(const Savgol2DFilter* f, const float* in, int rows, int cols, in
                                        cudaMemcpyDeviceToHost, P.s_out), "D2H")) return -1;
         cudaEventRecord(P.e_out[s], P.s_out);
     }
-    return cuda_ok(cudaStreamSynchronize(P.s_out), "sync") && cuda_ok(cudaStreamSynchronize(P.s_k), "sync") ? 0 : -1;
+    return cuda_ok(cudaStreamSynchronize(P.s_out), "sync") && cuda_ok(cudaStreamSynchronize(P.s_k), "sync") &&
+           cuda_ok(cudaStreamSynchronize(P.s_in), "sync") ? 0 : -1;
 }
 
 }  // namespace
@@ -267,6 +281,7 @@ int savgol2d_apply_band_at(const Savgol2DFilter* filter, const float* input, int
         fprintf(stderr, "savgol2d_apply_band: halos must be 0 (image border) or half_window_y rows, band must not be empty\n");
         return -1;
     }
+    sge::DeviceGuard guard(input);
     if (!sge::device_ready(true)) return -1;
     if (sge::classify(input) != MemKind::Device || sge::classify(output) != MemKind::Device) {
         fprintf(stderr, "savgol2d_apply_band: band and output must be device pointers\n");
@@ -317,24 +332,69 @@ int savgol2d_apply_valid(const Savgol2DFilter* filter, const float* input, int r
 }
 
 // Convenience wrappers: one filter per requested component, as the reference composes them
-// (src/savgol2d.c:462-618).
+// (src/savgol2d.c:462-618).  The reference re-creates the filter (design matrix, normal equations, Cholesky) on
+// every call; here the filters of the most recent wrapper configurations stay alive in a small cache -- creation
+// is host work in the hundreds of microseconds, more than the kernel takes on a megapixel image.
+}  // extern "C"
+namespace {
+struct WrapKey {
+    int hx, hy, order, dx, dy;
+    float delta_x, delta_y;
+    bool operator==(const WrapKey& o) const
+    {
+        return hx == o.hx && hy == o.hy && order == o.order && dx == o.dx && dy == o.dy && delta_x == o.delta_x && delta_y == o.delta_y;
+    }
+};
+struct WrapEntry { WrapKey key; Savgol2DFilter* f; unsigned long long used; };
+std::mutex g_wrap_mu;
+std::vector<WrapEntry> g_wrap;   // filters are immutable and apply is thread-safe: entries are shared, never destroyed while cached
+unsigned long long g_wrap_clock = 0;
+constexpr size_t kWrapCache = 16;
+
+// dx < 0 marks the fused Laplacian table (made by `make`)
+template <class Make>
+Savgol2DFilter* cached_filter(const WrapKey& key, Make make)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_wrap_mu);
+        for (auto& e : g_wrap)
+            if (e.key == key) { e.used = ++g_wrap_clock; return e.f; }
+    }
+    Savgol2DFilter* f = make();
+    if (!f) return nullptr;
+    std::lock_guard<std::mutex> lk(g_wrap_mu);
+    for (auto& e : g_wrap)
+        if (e.key == key) { e.used = ++g_wrap_clock; return e.f; }   // another thread was faster: both filters are equivalent, the
+                                                                      // spare one stays alive (a few KB) for callers that already hold it
+    if (g_wrap.size() >= kWrapCache) {
+        size_t lru = 0;
+        for (size_t i = 1; i < g_wrap.size(); ++i)
+            if (g_wrap[i].used < g_wrap[lru].used) lru = i;
+        g_wrap.erase(g_wrap.begin() + static_cast<long>(lru));   // evicted filters are not destroyed: a concurrent call may still use them
+    }
+    g_wrap.push_back({key, f, ++g_wrap_clock});
+    return f;
+}
+}  // namespace
+extern "C" {
+
 static int component(int hx, int hy, int order, int dx, int dy, const float* in, int rows, int cols, int stride, float* out,
                      float delta_x, float delta_y, Savgol2DBoundary boundary)
 {
-    Savgol2DConfig cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.half_window_x = static_cast<uint8_t>(hx);
-    cfg.half_window_y = static_cast<uint8_t>(hy);
-    cfg.poly_order = static_cast<uint8_t>(order);
-    cfg.deriv_x = static_cast<uint8_t>(dx);
-    cfg.deriv_y = static_cast<uint8_t>(dy);
-    cfg.delta_x = delta_x;
-    cfg.delta_y = delta_y;
-    Savgol2DFilter* f = savgol2d_create(&cfg);
+    Savgol2DFilter* f = cached_filter(WrapKey{hx, hy, order, dx, dy, delta_x, delta_y}, [&]() -> Savgol2DFilter* {
+        Savgol2DConfig cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.half_window_x = static_cast<uint8_t>(hx);
+        cfg.half_window_y = static_cast<uint8_t>(hy);
+        cfg.poly_order = static_cast<uint8_t>(order);
+        cfg.deriv_x = static_cast<uint8_t>(dx);
+        cfg.deriv_y = static_cast<uint8_t>(dy);
+        cfg.delta_x = delta_x;
+        cfg.delta_y = delta_y;
+        return savgol2d_create(&cfg);
+    });
     if (!f) return -1;
-    const int rc = savgol2d_apply(f, in, rows, cols, stride, out, stride, boundary);
-    savgol2d_destroy(f);
-    return rc;
+    return savgol2d_apply(f, in, rows, cols, stride, out, stride, boundary);
 }
 
 int savgol2d_gradient(int hx, int hy, int order, const float* input, int rows, int cols, int stride,
@@ -397,45 +457,43 @@ int savgol2d_laplacian(int hx, int hy, int order, const float* input, int rows, 
     // single pass (one image read, one write) instead of two filters plus an add
     // (ref composition: src/savgol2d.c:560-618; the exact flavour below keeps that composition).
     if (!sge::exact_mode()) {
-        Savgol2DConfig cxx, cyy;
-        memset(&cxx, 0, sizeof(cxx));
-        cxx.half_window_x = static_cast<uint8_t>(hx); cxx.half_window_y = static_cast<uint8_t>(hy);
-        cxx.poly_order = static_cast<uint8_t>(order); cxx.deriv_x = 2; cxx.deriv_y = 0;
-        cxx.delta_x = delta_x; cxx.delta_y = delta_y;
-        cyy = cxx; cyy.deriv_x = 0; cyy.deriv_y = 2;
-        if (!savgol2d_config_valid(&cxx) || !savgol2d_config_valid(&cyy)) {
-            fprintf(stderr, "savgol2d_create: invalid configuration\n");
-            return -1;
-        }
-        const int area = (2 * hx + 1) * (2 * hy + 1);
-        std::vector<float> wxx(area), wyy(area), wl(area);
-        double kxx[28], kyy[28], kl[28];
-        if (sgc::weights2d(hx, hy, order, 2, 0, wxx.data(), kxx) && sgc::weights2d(hx, hy, order, 0, 2, wyy.data(), kyy)) {
+        Savgol2DFilter* fl = cached_filter(WrapKey{hx, hy, order, -1, -1, delta_x, delta_y}, [&]() -> Savgol2DFilter* {
+            Savgol2DConfig cxx, cyy;
+            memset(&cxx, 0, sizeof(cxx));
+            cxx.half_window_x = static_cast<uint8_t>(hx); cxx.half_window_y = static_cast<uint8_t>(hy);
+            cxx.poly_order = static_cast<uint8_t>(order); cxx.deriv_x = 2; cxx.deriv_y = 0;
+            cxx.delta_x = delta_x; cxx.delta_y = delta_y;
+            cyy = cxx; cyy.deriv_x = 0; cyy.deriv_y = 2;
+            if (!savgol2d_config_valid(&cxx) || !savgol2d_config_valid(&cyy)) {
+                fprintf(stderr, "savgol2d_create: invalid configuration\n");
+                return nullptr;
+            }
+            const int area = (2 * hx + 1) * (2 * hy + 1);
+            std::vector<float> wxx(area), wyy(area), wl(area);
+            double kxx[28], kyy[28], kl[28];
+            if (!sgc::weights2d(hx, hy, order, 2, 0, wxx.data(), kxx) || !sgc::weights2d(hx, hy, order, 0, 2, wyy.data(), kyy)) return nullptr;
             const double sxx = static_cast<double>(sgc::scale2d(2, 0, delta_x, delta_y));
             const double syy = static_cast<double>(sgc::scale2d(0, 2, delta_x, delta_y));
             for (int k = 0; k < area; ++k) wl[k] = static_cast<float>(wxx[k] * sxx + wyy[k] * syy);
             for (int k = 0; k < 28; ++k) kl[k] = kxx[k] * sxx + kyy[k] * syy;
             Filter2DImpl* fi = static_cast<Filter2DImpl*>(calloc(1, sizeof(Filter2DImpl)));
             float* wt = static_cast<float*>(malloc(static_cast<size_t>(area) * sizeof(float)));
-            if (fi && wt) {
-                memcpy(wt, wl.data(), static_cast<size_t>(area) * sizeof(float));
-                fi->pub.config = cxx;
-                fi->pub.window_width = 2 * hx + 1; fi->pub.window_height = 2 * hy + 1; fi->pub.window_area = area;
-                fi->pub.num_terms = savgol2d_num_terms(order);
-                fi->pub.scale = 1.0f;   // both scales are folded into the table
-                fi->pub.weights = wt;
-                sg2d::plan_separable(hx, hy, order, kl, wt, &fi->plan);
-                fi->magic = kMagic2D;
-                {
-                    std::lock_guard<std::mutex> lk(g_mu2d);
-                    g_live2d.insert(fi);
-                }
-                const int rcf = savgol2d_apply(&fi->pub, input, rows, cols, stride, output, stride, boundary);
-                savgol2d_destroy(&fi->pub);
-                return rcf;
+            if (!fi || !wt) { free(fi); free(wt); return nullptr; }
+            memcpy(wt, wl.data(), static_cast<size_t>(area) * sizeof(float));
+            fi->pub.config = cxx;
+            fi->pub.window_width = 2 * hx + 1; fi->pub.window_height = 2 * hy + 1; fi->pub.window_area = area;
+            fi->pub.num_terms = savgol2d_num_terms(order);
+            fi->pub.scale = 1.0f;   // both scales are folded into the table
+            fi->pub.weights = wt;
+            sg2d::plan_separable(hx, hy, order, kl, wt, &fi->plan);
+            fi->magic = kMagic2D;
+            {
+                std::lock_guard<std::mutex> lk(g_mu2d);
+                g_live2d.insert(fi);
             }
-            free(fi); free(wt);
-        }
+            return &fi->pub;
+        });
+        if (fl) return savgol2d_apply(fl, input, rows, cols, stride, output, stride, boundary);
     }
     int rc = component(hx, hy, order, 2, 0, input, rows, cols, stride, output, delta_x, delta_y, boundary);
     if (rc != 0) return rc;

@@ -7,6 +7,7 @@
 // one centred output per further sample, polynomial trailing edge on flush, boundary mode
 // ignored.  Per channel the carry state is the last 2n+1 samples (device memory,
 // double buffered); steady-state chunks run the 1D kernel with that history as the left pad.
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -75,19 +76,21 @@ unsigned grid_for(size_t work, int block)
 
 int stream_arith() { return sge::exact_mode() ? sg::ARITH_EXACTSEQ : sg::ARITH_FAST; }
 
-// device-pointer push; returns outputs per channel or -1
-long long push_device(SavgolMCStream* s, const float* in, size_t in_pitch, size_t K, float* out, size_t out_pitch,
-                      cudaStream_t st)
+// Device-pointer push of channels [c0, c0 + nc): `in` / `out` point at channel c0.  Does not advance the stream
+// (the caller flips the state buffers and the counters once all channel blocks are queued).  Returns outputs
+// per channel or -1.
+long long push_range(SavgolMCStream* s, size_t c0, size_t nc, const float* in, size_t in_pitch, size_t K, float* out,
+                     size_t out_pitch, cudaStream_t st)
 {
     const size_t T = s->received;
     const size_t ws = static_cast<size_t>(s->ws);
     const int n = s->n;
-    float* cur = s->state[s->cur];
-    float* nxt = s->state[s->cur ^ 1];
+    float* cur = s->state[s->cur] + c0 * ws;
+    float* nxt = s->state[s->cur ^ 1] + c0 * ws;
     long long produced;
 
     if (T + K < ws) {
-        state_append_kernel<<<grid_for(s->channels * ws, 256), 256, 0, st>>>(cur, nxt, in, in_pitch, s->channels, s->ws,
+        state_append_kernel<<<grid_for(nc * ws, 256), 256, 0, st>>>(cur, nxt, in, in_pitch, nc, s->ws,
                                                                                static_cast<int>(K));
         sg::g_launches.fetch_add(1);
         if (!cuda_ok(cudaGetLastError(), "state append")) return -1;
@@ -100,16 +103,16 @@ long long push_device(SavgolMCStream* s, const float* in, size_t in_pitch, size_
         float* tmp = nullptr;
         const size_t L = T + K;
         if (T > 0) {
-            if (!cuda_ok(cudaMallocAsync(&tmp, s->channels * L * sizeof(float), st), "cudaMallocAsync(first fill)")) return -1;
+            if (!cuda_ok(cudaMallocAsync(&tmp, nc * L * sizeof(float), st), "cudaMallocAsync(first fill)")) return -1;
             bool ok = cuda_ok(cudaMemcpy2DAsync(tmp, L * sizeof(float), cur + (ws - T), ws * sizeof(float), T * sizeof(float),
-                                                s->channels, cudaMemcpyDeviceToDevice, st), "gather state") &&
+                                                nc, cudaMemcpyDeviceToDevice, st), "gather state") &&
                       cuda_ok(cudaMemcpy2DAsync(tmp + T, L * sizeof(float), in, in_pitch * sizeof(float), K * sizeof(float),
-                                                s->channels, cudaMemcpyDeviceToDevice, st), "gather chunk");
+                                                nc, cudaMemcpyDeviceToDevice, st), "gather chunk");
             if (!ok) { cudaFreeAsync(tmp, st); return -1; }
             x = tmp; xp = L;
         }
         sge::Problem1D p{};
-        p.filter = s->filter; p.in = x; p.out = out; p.rows = s->channels; p.len = L;
+        p.filter = s->filter; p.in = x; p.out = out; p.rows = nc; p.len = L;
         p.in_row_bytes = xp * sizeof(float); p.out_row_bytes = out_pitch * sizeof(float);
         p.in_stride = p.out_stride = 4;
         p.mode = sg::MODE_POLY; p.edge_lead = true; p.edge_trail = false;
@@ -122,7 +125,7 @@ long long push_device(SavgolMCStream* s, const float* in, size_t in_pitch, size_
         produced = static_cast<long long>(L) - n;
     } else {
         sge::Problem1D p{};
-        p.filter = s->filter; p.in = in; p.out = out; p.rows = s->channels; p.len = K;
+        p.filter = s->filter; p.in = in; p.out = out; p.rows = nc; p.len = K;
         p.in_row_bytes = in_pitch * sizeof(float); p.out_row_bytes = out_pitch * sizeof(float);
         p.in_stride = p.out_stride = 4;
         p.lhalo = cur + 1; p.lhalo_pitch = ws;  // the 2n most recent samples
@@ -133,10 +136,23 @@ long long push_device(SavgolMCStream* s, const float* in, size_t in_pitch, size_
         if (!sge::run1d_device(p, st)) return -1;
         produced = static_cast<long long>(K);
     }
+    return produced;
+}
+
+void advance(SavgolMCStream* s, size_t K, long long produced)
+{
     s->cur ^= 1;
     s->received += K;
     s->emitted += static_cast<size_t>(produced);
-    return produced;
+}
+
+bool on_stream_device(const SavgolMCStream* s, const char* who)
+{
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (dev == s->device) return true;
+    fprintf(stderr, "%s: the stream lives on device %d but device %d is current\n", who, s->device, dev);
+    return false;
 }
 
 }  // namespace
@@ -190,38 +206,65 @@ long long savgol_mcstream_push(SavgolMCStream* s, const float* input, size_t in_
                                float* output, size_t out_pitch)
 {
     if (!s || !input || !output || chunk_len == 0) return -1;
+    // the chunk that first fills the window emits up to chunk_len + half_window outputs per channel
     if (in_pitch < chunk_len || out_pitch < chunk_len + static_cast<size_t>(s->n)) {
-        if (s->channels > 1 || out_pitch < chunk_len) {
-            fprintf(stderr, "savgol_mcstream_push: need in_pitch >= chunk_len and out_pitch >= chunk_len + half_window\n");
-            return -1;
-        }
+        fprintf(stderr, "savgol_mcstream_push: need in_pitch >= chunk_len and out_pitch >= chunk_len + half_window\n");
+        return -1;
     }
+    if (!on_stream_device(s, "savgol_mcstream_push")) return -1;
     cudaStream_t st = sge::current_stream();
     const MemKind ki = sge::classify(input), ko = sge::classify(output);
-    if (ki == MemKind::Device && ko == MemKind::Device) return push_device(s, input, in_pitch, chunk_len, output, out_pitch, st);
+    if (ki == MemKind::Device && ko == MemKind::Device) {
+        const long long produced = push_range(s, 0, s->channels, input, in_pitch, chunk_len, output, out_pitch, st);
+        if (produced >= 0) advance(s, chunk_len, produced);
+        return produced;
+    }
     if (ki == MemKind::Device || ko == MemKind::Device) {
         fprintf(stderr, "savgol_b200: input and output must both be device pointers or both be host pointers\n");
         return -1;
     }
-    // host chunks: stage the whole chunk (channels x K) through device scratch
-    const size_t opitch = chunk_len + static_cast<size_t>(s->ws);
-    float *din = nullptr, *dout = nullptr;
-    bool ok = cuda_ok(cudaMallocAsync(&din, s->channels * chunk_len * sizeof(float), st), "cudaMallocAsync") &&
-              cuda_ok(cudaMallocAsync(&dout, s->channels * opitch * sizeof(float), st), "cudaMallocAsync");
-    long long produced = -1;
-    if (ok) ok = cuda_ok(cudaMemcpy2DAsync(din, chunk_len * sizeof(float), input, in_pitch * sizeof(float),
-                                           chunk_len * sizeof(float), s->channels, cudaMemcpyHostToDevice, st), "H2D");
-    if (ok) {
-        produced = push_device(s, din, chunk_len, chunk_len, dout, opitch, st);
-        ok = produced >= 0;
+    // Host chunks: blocks of channels travel through the three-slot staging pipeline (H2D of block i+1 and D2H of
+    // block i-1 overlap the kernel of block i).  The carry state stays on the device; the blocks' kernels run in
+    // order on one stream and touch disjoint channels of it.  Work queued earlier on the caller's stream (a
+    // previous device push, a reset) is ordered before the first block.
+    sge::PipeLease lease;
+    if (!lease.ok()) return -1;
+    sge::Pipeline& P = *lease;
+    const size_t K = chunk_len;
+    const size_t opitch = (K + static_cast<size_t>(s->ws) + 3) & ~static_cast<size_t>(3);   // 16-byte aligned rows
+    const size_t cb = std::max<size_t>(1, std::min(s->channels, sge::chunk_floats() / opitch));
+    if (!P.ensure(cb * K, cb * opitch)) return -1;
+    cudaEvent_t prior = nullptr;
+    if (cudaEventCreateWithFlags(&prior, cudaEventDisableTiming) == cudaSuccess) {
+        cudaEventRecord(prior, st);
+        cudaStreamWaitEvent(P.s_k, prior, 0);
+        cudaEventDestroy(prior);
     }
-    if (ok && produced > 0)
-        ok = cuda_ok(cudaMemcpy2DAsync(output, out_pitch * sizeof(float), dout, opitch * sizeof(float),
-                                       static_cast<size_t>(produced) * sizeof(float), s->channels, cudaMemcpyDeviceToHost, st), "D2H");
-    if (ok) ok = cuda_ok(cudaStreamSynchronize(st), "sync");
-    if (din) cudaFreeAsync(din, st);
-    if (dout) cudaFreeAsync(dout, st);
-    return ok ? produced : -1;
+    long long produced = -1;
+    size_t c0 = 0;
+    for (size_t b = 0; c0 < s->channels; ++b, c0 += cb) {
+        const int sl = static_cast<int>(b % sge::Pipeline::kSlots);
+        const size_t nc = std::min(cb, s->channels - c0);
+        if (b >= sge::Pipeline::kSlots && !cuda_ok(cudaStreamWaitEvent(P.s_in, P.e_out[sl], 0), "wait")) return -1;
+        if (!cuda_ok(cudaMemcpy2DAsync(P.d_in[sl], K * sizeof(float), input + c0 * in_pitch, in_pitch * sizeof(float), K * sizeof(float), nc,
+                                       cudaMemcpyHostToDevice, P.s_in), "H2D")) return -1;
+        cudaEventRecord(P.e_in[sl], P.s_in);
+        cudaStreamWaitEvent(P.s_k, P.e_in[sl], 0);
+        if (b >= sge::Pipeline::kSlots) cudaStreamWaitEvent(P.s_k, P.e_out[sl], 0);
+        const long long k = push_range(s, c0, nc, P.d_in[sl], K, K, P.d_out[sl], opitch, P.s_k);
+        if (k < 0) { cudaStreamSynchronize(P.s_k); return -1; }
+        produced = k;
+        cudaEventRecord(P.e_k[sl], P.s_k);
+        cudaStreamWaitEvent(P.s_out, P.e_k[sl], 0);
+        if (k > 0 && !cuda_ok(cudaMemcpy2DAsync(output + c0 * out_pitch, out_pitch * sizeof(float), P.d_out[sl], opitch * sizeof(float),
+                                                static_cast<size_t>(k) * sizeof(float), nc, cudaMemcpyDeviceToHost, P.s_out), "D2H")) return -1;
+        cudaEventRecord(P.e_out[sl], P.s_out);
+    }
+    const bool ok = cuda_ok(cudaStreamSynchronize(P.s_out), "sync") && cuda_ok(cudaStreamSynchronize(P.s_k), "sync") &&
+                    cuda_ok(cudaStreamSynchronize(P.s_in), "sync");
+    if (!ok) return -1;
+    advance(s, K, produced);
+    return produced;
 }
 
 long long savgol_mcstream_flush(SavgolMCStream* s, float* output, size_t out_pitch)
@@ -229,6 +272,7 @@ long long savgol_mcstream_flush(SavgolMCStream* s, float* output, size_t out_pit
     if (!s || !output) return -1;
     if (s->received < static_cast<size_t>(s->ws)) return 0;
     if (out_pitch < static_cast<size_t>(s->n) && s->channels > 1) return -1;
+    if (!on_stream_device(s, "savgol_mcstream_flush")) return -1;
     cudaStream_t st = sge::current_stream();
     float* temp_edges = nullptr;
     const float* et = sge::edge_table_device(s->filter, st, &temp_edges);
@@ -285,6 +329,7 @@ long long savgol_mcstream_save(SavgolMCStream* s, void* blob, size_t capacity)
 {
     const size_t need = savgol_mcstream_checkpoint_size(s);
     if (!s || !blob || capacity < need) return -1;
+    if (!on_stream_device(s, "savgol_mcstream_save")) return -1;
     McCheckpoint h{kCkptMagic, 1u, s->channels, s->received, s->emitted, s->n, s->ws};
     std::memcpy(blob, &h, sizeof h);
     cudaStream_t st = sge::current_stream();
@@ -300,13 +345,17 @@ int savgol_mcstream_restore(SavgolMCStream* s, const void* blob, size_t bytes)
     if (!s || !blob || bytes < sizeof(McCheckpoint)) return -1;
     McCheckpoint h;
     std::memcpy(&h, blob, sizeof h);
-    if (h.magic != kCkptMagic || h.version != 1u || h.channels != s->channels || h.n != s->n || h.ws != s->ws ||
-        bytes < savgol_mcstream_checkpoint_size(s)) {
+    const size_t need = savgol_mcstream_checkpoint_size(s);
+    // a buffer larger than the checkpoint (the caller's capacity, trailing data) is fine: exactly the carry state
+    // of THIS stream is read, never more
+    if (h.magic != kCkptMagic || h.version != 1u || h.channels != s->channels || h.n != s->n || h.ws != s->ws || bytes < need ||
+        h.emitted > h.received) {
         std::fprintf(stderr, "savgol_mcstream_restore: checkpoint does not match this stream\n");
         return -1;
     }
+    if (!on_stream_device(s, "savgol_mcstream_restore")) return -1;
     cudaStream_t st = sge::current_stream();
-    if (!cuda_ok(cudaMemcpyAsync(s->state[s->cur], static_cast<const char*>(blob) + sizeof h, bytes - sizeof h, cudaMemcpyHostToDevice, st),
+    if (!cuda_ok(cudaMemcpyAsync(s->state[s->cur], static_cast<const char*>(blob) + sizeof h, need - sizeof h, cudaMemcpyHostToDevice, st),
                  "checkpoint H2D") ||
         !cuda_ok(cudaStreamSynchronize(st), "sync"))
         return -1;

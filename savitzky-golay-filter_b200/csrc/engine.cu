@@ -17,8 +17,9 @@ namespace {
 std::mutex g_reg_mu;
 std::unordered_set<const void*> g_live;
 thread_local cudaStream_t t_stream = nullptr;
-std::atomic<int> g_exact{0};
-std::atomic<int> g_dev_state{0};  // 0 unknown, 1 ok, -1 unusable
+std::atomic<int> g_exact{0};              // process default of the arithmetic flavour
+thread_local int t_exact = -1;            // the calling thread's own choice (-1: follow the process default)
+std::atomic<int> g_dev_state[kMaxDevices + 1];  // per device: 0 unknown, 1 ok, -1 unusable (last entry: "no device at all")
 }  // namespace
 
 void register_filter(FilterImpl* f)
@@ -48,20 +49,18 @@ bool cuda_ok(cudaError_t e, const char* what)
 
 bool device_ready(bool complain)
 {
-    int st = g_dev_state.load();
-    if (st == 0) {
-        int n = 0;
-        cudaError_t e = cudaGetDeviceCount(&n);
-        st = (e == cudaSuccess && n > 0) ? 1 : -1;
-        if (st == 1) {
-            int dev = 0, major = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
-            if (major != 10) st = -1;  // the fatbin holds sm_100a code only
+    int dev = -1;
+    int st = -1;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < kMaxDevices) {
+        st = g_dev_state[dev].load();
+        if (st == 0) {
+            int major = 0;
+            const cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+            st = (e == cudaSuccess && major == 10) ? 1 : -1;   // the fatbin holds sm_100a code only
+            g_dev_state[dev].store(st);
         }
-        (void)cudaGetLastError();
-        g_dev_state.store(st);
     }
+    (void)cudaGetLastError();
     if (st != 1 && complain)
         fprintf(stderr, "savgol_b200: no usable CUDA device (need compute capability 10.x); there is no CPU fallback\n");
     return st == 1;
@@ -80,11 +79,8 @@ MemKind classify(const void* p)
     }
 }
 
-Pipeline g_pipe;
-std::mutex g_pipe_mu;
-
 cudaStream_t current_stream() { return t_stream; }
-int exact_mode() { return g_exact.load(std::memory_order_relaxed); }
+int exact_mode() { return t_exact >= 0 ? t_exact : g_exact.load(std::memory_order_relaxed); }
 
 // ---------------------------------------------------------------------------------------------
 const float* edge_table_device(const SavgolFilter* f, cudaStream_t stream, float** temp)
@@ -240,8 +236,9 @@ void savgol_b200_set_stream(void* s) { sge::t_stream = static_cast<cudaStream_t>
 void* savgol_b200_get_stream(void) { return sge::t_stream; }
 unsigned long long savgol_b200_launch_count(void) { return sg::g_launches.load(); }
 unsigned long long savgol_b200_tma_launch_count(void) { return sg::g_tma_launches.load(); }
-void savgol_b200_set_tma(int on) { sg::g_tma_enabled.store(on ? 1 : 0); }
-void savgol_b200_set_exact(int exact) { sge::g_exact.store(exact ? 1 : 0); }
-int savgol_b200_get_exact(void) { return sge::g_exact.load(); }
+void savgol_b200_set_tma(int how) { sg::g_tma_enabled.store(how < 0 ? 0 : how > 2 ? 2 : how); }
+void savgol_b200_set_exact(int exact) { sge::t_exact = exact ? 1 : 0; }
+void savgol_b200_set_exact_default(int exact) { sge::g_exact.store(exact ? 1 : 0); }
+int savgol_b200_get_exact(void) { return sge::exact_mode(); }
 
 }  // extern "C"

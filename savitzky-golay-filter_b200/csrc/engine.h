@@ -33,7 +33,7 @@ enum class MemKind { Device, Pinned, Pageable };
 MemKind classify(const void* p);
 
 cudaStream_t current_stream();
-bool device_ready(bool complain);
+bool device_ready(bool complain);   // the CURRENT device is a compute-capability 10.x part
 int exact_mode();
 
 // Logs "savgol_b200: <what>: <cuda error>" and returns false when e != cudaSuccess.
@@ -65,6 +65,7 @@ const float* edge_table_device(const SavgolFilter* f, cudaStream_t stream, float
 // Host-buffer staging.  Three device slots form a ring; H2D, kernel and D2H of consecutive
 // chunks overlap on three streams.  Pinned host memory is DMA'd directly; pageable memory goes
 // through the driver's staging (cudaMemcpyAsync degrades gracefully to a synchronous copy).
+// A pipeline belongs to ONE device and is used by ONE host-pointer call at a time (PipeLease).
 struct Pipeline {
     static constexpr int kSlots = 3;
     int dev = -1;
@@ -74,53 +75,51 @@ struct Pipeline {
     float* d_out[kSlots] = {};
     size_t cap_in = 0, cap_out = 0;  // floats per slot
 
-    bool ensure(size_t need_in, size_t need_out)
-    {
-        int cur = 0;
-        if (!sge::cuda_ok(cudaGetDevice(&cur), "cudaGetDevice")) return false;
-        if (dev != cur) { release(); dev = cur; }
-        if (!s_in) {
-            if (!sge::cuda_ok(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking), "stream")) return false;
-            if (!sge::cuda_ok(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking), "stream")) return false;
-            if (!sge::cuda_ok(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking), "stream")) return false;
-            for (int i = 0; i < kSlots; ++i) {
-                cudaEventCreateWithFlags(&e_in[i], cudaEventDisableTiming);
-                cudaEventCreateWithFlags(&e_k[i], cudaEventDisableTiming);
-                cudaEventCreateWithFlags(&e_out[i], cudaEventDisableTiming);
-            }
-        }
-        if (need_in > cap_in) {
-            for (int i = 0; i < kSlots; ++i) { cudaFree(d_in[i]); d_in[i] = nullptr; }
-            for (int i = 0; i < kSlots; ++i)
-                if (!sge::cuda_ok(cudaMalloc(&d_in[i], need_in * sizeof(float)), "cudaMalloc(staging in)")) return false;
-            cap_in = need_in;
-        }
-        if (need_out > cap_out) {
-            for (int i = 0; i < kSlots; ++i) { cudaFree(d_out[i]); d_out[i] = nullptr; }
-            for (int i = 0; i < kSlots; ++i)
-                if (!sge::cuda_ok(cudaMalloc(&d_out[i], need_out * sizeof(float)), "cudaMalloc(staging out)")) return false;
-            cap_out = need_out;
-        }
-        return true;
-    }
-    void release()
-    {
-        for (int i = 0; i < kSlots; ++i) {
-            if (d_in[i]) cudaFree(d_in[i]);
-            if (d_out[i]) cudaFree(d_out[i]);
-            d_in[i] = d_out[i] = nullptr;
-            if (e_in[i]) { cudaEventDestroy(e_in[i]); cudaEventDestroy(e_k[i]); cudaEventDestroy(e_out[i]); }
-            e_in[i] = e_k[i] = e_out[i] = nullptr;
-        }
-        if (s_in) { cudaStreamDestroy(s_in); cudaStreamDestroy(s_k); cudaStreamDestroy(s_out); }
-        s_in = s_k = s_out = nullptr;
-        cap_in = cap_out = 0;
-    }
+    // Streams / events on first use, slots grown on demand.  The current device must be `dev`.
+    bool ensure(size_t need_in, size_t need_out);
+    void release();
 };
 
+// Lease of an idle pipeline of the CURRENT device for the duration of one host-pointer call.  Concurrent
+// calls (several host threads, several devices) each get their own pipeline: nothing serialises them
+// except the PCIe link itself.  Returned pipelines are kept for reuse (a few per device).
+class PipeLease {
+  public:
+    PipeLease();
+    ~PipeLease();
+    PipeLease(const PipeLease&) = delete;
+    PipeLease& operator=(const PipeLease&) = delete;
+    bool ok() const { return p_ != nullptr; }
+    Pipeline* operator->() const { return p_; }
+    Pipeline& operator*() const { return *p_; }
 
+  private:
+    Pipeline* p_ = nullptr;
+};
 
-extern Pipeline g_pipe;      // one per process, guarded by g_pipe_mu (host-pointer calls serialise)
-extern std::mutex g_pipe_mu;
+// Makes the device that owns `ptr` current for the lifetime of the guard (no-op for host pointers and when it
+// already is current).
+class DeviceGuard {
+  public:
+    explicit DeviceGuard(const void* ptr);
+    explicit DeviceGuard(int device);
+    ~DeviceGuard();
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+
+  private:
+    int prev_ = -1;
+};
+
+// Host staging of one long signal: outputs [a, b) of x[0..L) into y (y[0] <-> output a), cut into pieces
+// with explicit n-sample halos; samples outside [0, L) follow `mode` / the polynomial edges as in savgol_apply.
+// Alias safe: y may be x + a (in place).
+bool run1d_host_range(Pipeline& P, const SavgolFilter* f, const float* x, size_t L, size_t a, size_t b, float* y,
+                      int mode, bool poly_edges, int arith);
+// Batch of contiguous-sample rows in HOST memory (chunks of whole rows, or run1d_host_range per row when a row
+// is longer than a staging chunk).  Uses a pipeline of the current device.
+bool run1d_host(const SavgolFilter* f, const float* in, float* out, size_t rows, size_t len, size_t in_pitch,
+                size_t out_pitch, int mode, bool poly_edges, int arith);
+size_t chunk_floats();
 
 }  // namespace sge

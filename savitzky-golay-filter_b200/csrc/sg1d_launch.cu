@@ -31,29 +31,6 @@ const Kernel1D* sg1d_group_table(int group)
     }
 }
 
-const Kernel1DTma* sg1d_tma_group_table(int group)
-{
-    switch (group) {
-        case 0: return sg1d_tma_group_table_0();
-        case 1: return sg1d_tma_group_table_1();
-        case 2: return sg1d_tma_group_table_2();
-        case 3: return sg1d_tma_group_table_3();
-        case 4: return sg1d_tma_group_table_4();
-        case 5: return sg1d_tma_group_table_5();
-        case 6: return sg1d_tma_group_table_6();
-        case 7: return sg1d_tma_group_table_7();
-        default: return nullptr;
-    }
-}
-
-namespace {
-struct GridInfo { int blocks_per_sm = 0; };
-GridInfo g_grid_tma[kMaxN + 1][VT_COUNT];
-
-// cuTensorMapEncodeTiled, resolved at run time (the library has to load on machines without libcuda).
-typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiled encode_tiled()
 {
     static std::atomic<EncodeTiled> s_fn{nullptr};
@@ -73,6 +50,26 @@ EncodeTiled encode_tiled()
     return s_state.load(std::memory_order_acquire) == 1 ? s_fn.load(std::memory_order_acquire) : nullptr;
 }
 
+
+const Kernel1DTma* sg1d_tma_group_table(int group)
+{
+    switch (group) {
+        case 0: return sg1d_tma_group_table_0();
+        case 1: return sg1d_tma_group_table_1();
+        case 2: return sg1d_tma_group_table_2();
+        case 3: return sg1d_tma_group_table_3();
+        case 4: return sg1d_tma_group_table_4();
+        case 5: return sg1d_tma_group_table_5();
+        case 6: return sg1d_tma_group_table_6();
+        case 7: return sg1d_tma_group_table_7();
+        default: return nullptr;
+    }
+}
+
+namespace {
+struct GridInfo { int blocks_per_sm = 0; };
+GridInfo g_grid_tma[kMaxN + 1][VT_COUNT];
+
 // {32 floats, nrows, rows} view of a batch of contiguous rows, 128-byte swizzle, box of `box_rows` tensor rows.
 bool encode_rows(EncodeTiled enc, CUtensorMap* m, const void* base, unsigned long long nrows, unsigned long long rows,
                  unsigned long long row_bytes, unsigned box_rows)
@@ -86,16 +83,25 @@ bool encode_rows(EncodeTiled enc, CUtensorMap* m, const void* base, unsigned lon
 }
 
 // The TMA kernels take contiguous fp32 rows of at least one segment whose base and pitch are 16-byte aligned.
-bool tma_eligible(int variant, const Args1D& a)
+// Whether they are FASTER than the cp.async kernels was measured on B200 (tools/r2_sweep1d.py, profiles/):
+// yes for half-windows up to 19 (the staging / store instructions they save are issue slots the FFMA2 stream
+// can use; +2 ... +8 %), no for the wide windows that are fp32-pipe bound anyway (20 ... 32: -2 ... -6 %, except
+// 26 where the cp.async instantiation is the slow one), and no for launches of fewer than ~2048 segments, where
+// the first tensor-map fetch is exposed latency.  g_tma_enabled: 0 off, 1 this rule, 2 always (tests).
+bool tma_eligible(int n, int variant, const Args1D& a)
 {
-    if (!g_tma_enabled.load(std::memory_order_relaxed) || (variant != V_BATCH_FAST && variant != V_STREAM_FAST)) return false;
+    const int how = g_tma_enabled.load(std::memory_order_relaxed);
+    if (how == 0 || (variant != V_BATCH_FAST && variant != V_STREAM_FAST)) return false;
     if (a.in_stride != 4 || a.out_stride != 4 || a.len < kTile) return false;
     if ((reinterpret_cast<uintptr_t>(a.in) | reinterpret_cast<uintptr_t>(a.out)) & 15) return false;
     if (a.rows > 1 && ((a.in_row_bytes | a.out_row_bytes) & 15)) return false;
     if (a.rows >= (1LL << 31) || a.len >= (1LL << 36) || a.in_row_bytes >= (1LL << 40) || a.out_row_bytes >= (1LL << 40)) return false;
+    if (how == 1) {
+        if (!(n <= 19 || n == 26)) return false;
+        if (((a.len + kTile - 1) / kTile) * a.rows < 2048) return false;
+    }
     return true;
 }
-
 GridInfo g_grid[kMaxN + 1][V_COUNT][5];  // per (n, variant, packing); filled lazily (same value on every B200)
 int g_sms[64];
 std::mutex g_mu;
@@ -177,7 +183,7 @@ cudaError_t sg1d_launch(int n, int variant, const W1D& w, Args1D& a, cudaStream_
         return cudaErrorInvalidValue;
     }
     a.out_tma = 0;
-    if (a.pack_g == 0 && tma_eligible(variant, a)) {
+    if (a.pack_g == 0 && tma_eligible(n, variant, a)) {
         if (EncodeTiled enc = encode_tiled()) {
             const cudaError_t e = sg1d_launch_tma(enc, n, variant == V_STREAM_FAST ? VT_STREAM : VT_BATCH, w, a, stream);
             if (e != cudaErrorNotSupported) return e;   // NotSupported: the driver refused a tensor map -> generic kernel

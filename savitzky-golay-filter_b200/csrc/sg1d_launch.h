@@ -31,6 +31,13 @@ enum : int { VT_BATCH = 0, VT_STREAM = 1, VT_COUNT = 2 };
 const Kernel1D* sg1d_group_table(int group);
 const Kernel1DTma* sg1d_tma_group_table(int group);
 
+// cuTensorMapEncodeTiled, resolved at run time through the runtime's driver entry point table (the library has to
+// load on machines without libcuda).  nullptr when unavailable.
+typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiled encode_tiled();
+
 // Grid sizing + launch.  Returns cudaSuccess or the launch error.
 cudaError_t sg1d_launch(int n, int variant, const W1D& w, Args1D& args, cudaStream_t stream);
 

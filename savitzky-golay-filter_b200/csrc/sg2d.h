@@ -24,6 +24,7 @@ struct Args2D {
     long long n_images;
     int boundary;
     float scale;
+    int use_tma;            // separable kernel: the launcher encoded a tensor map of the input (aligned images only)
     int row0;               // image row of the buffer's first row (bands of a larger image; 0 otherwise)
     int band_rows;          // separable kernel: output rows per work item (set by the launcher)
     unsigned* counter;      // separable kernel: work-item ticket counter, zeroed in stream order before the launch

@@ -28,11 +28,14 @@
 //      warm-up rows per band.
 #pragma once
 #include <atomic>
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 #include "sg2d.h"
 #include "sg_common.cuh"
 #include "sg1d_kernel.cuh"  // static_for
+#include "sg1d_tma.cuh"     // mbarrier / bulk-tensor helpers
 
 namespace sg { extern std::atomic<unsigned long long> g_launches; }
 
@@ -85,6 +88,12 @@ struct SepW {
     float rk[R][16];        // rk[r][k-1]: weight of s_k = x[c+k] + sx * x[c-k], k = 1..n
     float col[R][33];       // column factor * scale, col[r][wy], wy = 0..2n
     float sx;               // +1 (even in x) / -1 (odd in x)
+};
+
+// Tensor map of the input images for the bulk-tensor (TMA) staging of interior work items: {cols, rows, images},
+// box = two staged rows of one strip (ROWF floats each), no swizzle.
+struct alignas(64) Tma2D {
+    CUtensorMap pair;
 };
 
 // Additive surface W(y,x) = u(x) + v(y) (sg2d_add.cu).  Row weights as pairs for the sample-broadcast FFMA2 form:
@@ -193,7 +202,7 @@ __device__ __noinline__ void stage_edge_pair(unsigned d, const float* r0, const 
 
 template <int N, int R, int RX, bool ADD>
 __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? ((N <= 6 || (N == 7 && (R == 2 || R == 3))) ? SG2D_MINB : 3) : ((N >= 15 && R >= 3) ? SG2D_WIDE_MINB : SG2D_MINB2)) sep_kernel(const __grid_constant__ typename WSel<R, ADD>::type w,
-                                                                            const __grid_constant__ Args2D a)
+                                                                            const __grid_constant__ Args2D a, const __grid_constant__ Tma2D maps)
 {
     static_assert(!ADD || (R == 1 && RX == 4 && N <= 8), "additive variant: one weight set, 4 columns per lane, static ring");
     constexpr int TW = 32 * RX;                 // output columns per strip
@@ -211,10 +220,24 @@ __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? (
     constexpr int VW = RX >= 4 ? 4 : 2;         // floats per shared load
     constexpr int NV = (WIN + VW - 1) / VW;
 
-    __shared__ __align__(16) float s_ring[kWarps][kRing][ROWF];
+    // TMA staging needs 128-byte aligned destinations: two rows of a step are 2 * ROWF floats apart
+    constexpr bool TMA_OK = (2 * ROWF * 4) % 128 == 0;
+    __shared__ __align__(128) float s_ring[kWarps][kRing][ROWF];
+    __shared__ __align__(8) unsigned long long s_mbar[kWarps][kRing / 2];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float(*ring)[ROWF] = s_ring[warp];
+    const unsigned mbar0 = sg::smem_u32(&s_mbar[warp][0]);
+    unsigned par_bits = 0;   // per mbarrier: the phase parity its next completion will have
+    if (TMA_OK && a.use_tma) {
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < kRing / 2; ++q) sg::mbar_init(mbar0 + 8 * q, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+            sg::fence_proxy_async();
+        }
+        __syncwarp();
+    }
 
     // 16-byte copies need aligned rows, whole chunks a width that is a multiple of 4; other images take the
     // out-of-line per-chunk path for every strip
@@ -294,9 +317,18 @@ __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? (
         // this lane's first chunk of the NEXT row to stage (interior bands)
         const float* src_next = in + static_cast<long long>(yin0) * a.in_stride + xb + 4 * lane;
         const float* const xbase = in + xb + 4 * lane;
+        // interior work item (no pad columns, no mapped rows) of an aligned image: one lane issues ONE bulk-tensor copy
+        // for the two rows of a step; it lands on the slot pair's mbarrier
+        const bool item_tma = TMA_OK && a.use_tma && simple_rows && x_in && y_in;
         auto stage_pair = [&](int t) {
             const int slot = t & (kRing - 1);
-            if (simple_rows) {
+            if (item_tma) {
+                if (lane == 0) {
+                    const unsigned mb = mbar0 + 8 * (slot >> 1);
+                    sg::mbar_expect_tx(mb, 2 * ROWF * 4);
+                    sg::tma_load_3d(ring_lane_s + slot * (ROWF * 4), &maps.pair, xb, yin0 + t, static_cast<int>(img), mb);
+                }
+            } else if (simple_rows) {
                 const float *s0, *s1;
                 if (y_in) {
                     s0 = src_next;
@@ -331,6 +363,17 @@ __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? (
                                              in + static_cast<long long>(map_index(yin0 + t + 1, a.rows, a.boundary)) * a.in_stride,
                                              xb, a.cols, a.boundary, lane);
             }
+        };
+        // rows t, t+1 have landed: this lane's cp.async copies, or the step's bulk-tensor copy
+        auto wait_pair = [&](int t) {
+            if (item_tma) {
+                const int q = (t & (kRing - 1)) >> 1;
+                sg::mbar_wait(mbar0 + 8 * q, (par_bits >> q) & 1u);
+                par_bits ^= 1u << q;
+            } else {
+                cp_async_wait<kAhead / 2 - 1>();
+            }
+            __syncwarp();   // ... and everybody else's; rows t-2, t-1 are fully consumed
         };
         // store side, hoisted: this lane's columns, whether they lie inside the stored region and
         // whether a vector store is legal; the row pointer advances by the output pitch per emitted row
@@ -472,8 +515,7 @@ __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? (
             int phase = 0;
 #pragma unroll 1
             for (int t = 0; t < steps2; t += 2) {
-                cp_async_wait<kAhead / 2 - 1>();
-                __syncwarp();
+                wait_pair(t);
                 if (t + kAhead < steps2) stage_pair(t + kAhead);
                 cp_async_commit();
 
@@ -520,6 +562,8 @@ __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? (
                     }
                 });
                 phase = phase + 1 == NA / 2 ? 0 : phase + 1;
+                // (stores stay OUTSIDE the phases: one copy of the store code and two register moves per value measured
+                // 4 % faster than a store inside each of the n+1 phases -- the loop body must stay small)
                 const unsigned te = static_cast<unsigned>(t - 2 * N - shift);   // output row completed by row t
                 if (te < static_cast<unsigned>(nrows)) emit(v0);
                 if (te + 1u < static_cast<unsigned>(nrows)) emit(v1);
@@ -532,8 +576,7 @@ __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? (
             int phase = 0;
 #pragma unroll 1
             for (int t = 0; t < steps2; t += 2) {
-                cp_async_wait<kAhead / 2 - 1>();   // rows t and t+1 have landed (this lane's part) ...
-                __syncwarp();                      // ... and everybody else's; rows t-2, t-1 are fully consumed
+                wait_pair(t);
                 if (t + kAhead < steps2) stage_pair(t + kAhead);   // into the slots of rows t-2, t-1
                 cp_async_commit();
 
@@ -584,8 +627,7 @@ __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? (
                 for (int u = 0; u < kU; u += 2) {
                     const int t = tb * kU + u;
                     if (t < steps2) {
-                        cp_async_wait<kAhead / 2 - 1>();   // rows t and t+1 have landed (this lane's part) ...
-                        __syncwarp();                      // ... and everybody else's; rows t-2, t-1 are fully consumed
+                        wait_pair(t);
                         if (t + kAhead < steps2) stage_pair(t + kAhead);   // into the slots of rows t-2, t-1
                         cp_async_commit();
 
@@ -692,12 +734,38 @@ cudaError_t launch_nr(const Args2D& a, const SepPlan& plan, cudaStream_t stream)
     const long long items = strips * bands * a.n_images;
     if (items <= 0) return cudaSuccess;
     if (items >= (1LL << 31)) return cudaErrorInvalidValue;
+    // bulk-tensor staging of interior work items: the images as a {cols, rows, images} tensor, box = the two rows a
+    // step consumes.  Only where the kernel's row ring keeps the destinations 128-byte aligned and the image layout
+    // meets the tensor-map rules (16-byte aligned base and strides); everything else stages with cp.async.
+    Tma2D maps;
+    std::memset(&maps, 0, sizeof(maps));
+    aa.use_tma = 0;
+    {
+        constexpr int PADX = (N + 3) & ~3;
+        constexpr int ROWF = TW + 2 * PADX;
+        static const bool off = [] { const char* e = std::getenv("SAVGOL_B200_NO_TMA2D"); return e && e[0] == '1'; }();
+        if ((2 * ROWF * 4) % 128 == 0 && !off && ((reinterpret_cast<uintptr_t>(a.in) & 15) | (a.in_stride & 3) | (a.in_image_pitch & 3) | (a.cols & 3)) == 0 &&
+            a.cols >= ROWF && a.rows >= 2) {
+            if (sg::EncodeTiled enc = sg::encode_tiled()) {
+                const cuuint64_t dims[3] = {static_cast<cuuint64_t>(a.cols), static_cast<cuuint64_t>(a.rows), static_cast<cuuint64_t>(a.n_images)};
+                const cuuint64_t strides[2] = {static_cast<cuuint64_t>(a.in_stride) * 4,
+                                               a.n_images > 1 ? static_cast<cuuint64_t>(a.in_image_pitch) * 4
+                                                              : static_cast<cuuint64_t>(a.in_stride) * 4 * static_cast<cuuint64_t>(a.rows)};
+                const cuuint32_t box[3] = {static_cast<cuuint32_t>(ROWF), 2, 1};
+                const cuuint32_t es[3] = {1, 1, 1};
+                if (strides[1] < (1ull << 40) && strides[0] < (1ull << 40) &&
+                    enc(&maps.pair, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(a.in), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+                    aa.use_tma = 1;
+            }
+        }
+    }
     cudaError_t ec = acquire_counter(stream, &aa.counter);
     if (ec != cudaSuccess) return ec;
     long long grid = static_cast<long long>(sms) * bps;
     const long long need = (items + kWarps - 1) / kWarps;
     if (grid > need) grid = need;
-    kern<<<static_cast<unsigned>(grid), kWarps * 32, 0, stream>>>(w, aa);
+    kern<<<static_cast<unsigned>(grid), kWarps * 32, 0, stream>>>(w, aa, maps);
     sg::g_launches.fetch_add(1);
     ec = cudaGetLastError();
     const cudaError_t ef = cudaFreeAsync(aa.counter, stream);

@@ -136,6 +136,43 @@ def test_scalar_stream_shim_bit_identical_to_oracle(oracle):
         s.close()
 
 
+def test_stream_flush_leading_matches_the_compiled_reference(oracle):
+    # ref: src/savgol_stream.c:254-275 -- re-emits the n leading-edge outputs from the CURRENT window contents (plain
+    # push skips them); compared call by call with the unmodified reference, including the counters and the
+    # max_count / not-yet-full / NULL conventions
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    R = oracle.ref()
+    rng = np.random.default_rng(7)
+    for n, m, d in [(5, 3, 0), (10, 2, 1), (3, 2, 2)]:
+        cfg = oracle.make_config(n, m, d, 0.5, 0)
+        rs = R.savgol_stream_create(C.byref(cfg))
+        s = sg.SavgolStream(n, m, d, 0.5)
+        rbuf = (C.c_float * 40)()
+        x = rng.standard_normal(2 * n + 9).astype(np.float32)
+        for i, v in enumerate(x):
+            if i < 2 * n + 1:   # window not full yet: nothing to re-emit, counters untouched
+                assert R.savgol_stream_flush_leading(rs, rbuf, 40) == 0 and s.flush_leading() == []
+            ok = C.c_bool(False)
+            R.savgol_stream_push(rs, float(v), C.byref(ok))
+            s.push(float(v))
+            if i >= 2 * n:
+                k = R.savgol_stream_flush_leading(rs, rbuf, 40)
+                mine = s.flush_leading()
+                assert k == n == len(mine)
+                assert np.array_equal(bits(np.array(mine, np.float32)), bits(np.array(rbuf[:k], np.float32))), (n, m, d, i)
+                assert R.savgol_stream_samples_output(rs) == s.samples_output
+        # max_count clamps, non-positive max_count and NULL return 0 (not -1, unlike flush)
+        lib = sg.lib()
+        small = (C.c_float * 2)()
+        assert lib.savgol_stream_flush_leading(s._h, small, 2) == R.savgol_stream_flush_leading(rs, rbuf, 2) == 2
+        assert np.array_equal(bits(np.array(small[:2], np.float32)), bits(np.array(rbuf[:2], np.float32)))
+        assert lib.savgol_stream_flush_leading(s._h, small, 0) == R.savgol_stream_flush_leading(rs, rbuf, 0) == 0
+        assert lib.savgol_stream_flush_leading(None, small, 2) == 0
+        R.savgol_stream_destroy(rs)
+        s.close()
+
+
 def test_apply_fails_loudly_without_gpu(capfd):
     if sg.device_ok():
         pytest.skip("GPU present")

@@ -43,3 +43,15 @@ def test_extension_api_from_plain_c():
     p = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stdout[-1500:] + p.stderr[-1500:]
     assert p.stdout.count("[PASS]") == 4 and "[FAIL]" not in p.stdout, p.stdout
+
+
+def test_multi_gpu_api_from_plain_c():
+    # examples/c_multi_gpu.c: savgol_apply_batch_multi (host batch sharded / one long signal partitioned) and
+    # savgol_apply_slices (device-resident slices, halos read from the neighbours' memory) from C99, each compared bit
+    # for bit with the single-GPU call.  With one visible GPU the device list repeats it.
+    exe = os.path.join(BIN, "c_multi_gpu_b200")
+    if not os.path.exists(exe):
+        pytest.skip("drop-in binaries not built")
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-1500:] + p.stderr[-1500:]
+    assert p.stdout.count("[PASS]") == 4 and "[FAIL]" not in p.stdout, p.stdout

@@ -1,0 +1,181 @@
+"""Host-buffer staging (pipelines, in place, VALID, stream chunks) and the single-process multi-GPU C ABI.
+
+The staging chunk is shrunk to 1 MiB in a child process (SAVGOL_B200_CHUNK_MIB is read once per process) so that
+modest arrays are cut into many pieces / channel blocks."""
+import ctypes as C
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+import savgol_b200 as sg  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def run_child(code):
+    env = dict(os.environ, SAVGOL_B200_CHUNK_MIB="1")
+    p = subprocess.run([sys.executable, "-c", "import sys; sys.path.insert(0, %r)\n" % ROOT + textwrap.dedent(code)],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    return p.stdout
+
+
+def test_host_long_signal_in_place_and_valid_many_pieces():
+    # with input == output the D2H of one piece used to overwrite the next piece's left halo
+    out = run_child("""
+        import numpy as np, savgol_b200 as sg
+        from oracle import oracle as O
+        rng = np.random.default_rng(3)
+        L = 5 * (1 << 18) + 12345                      # > 5 staging pieces of 1 MiB
+        for n, m, d, mode in [(16, 3, 1, "reflect"), (32, 4, 2, "periodic"), (7, 3, 0, "polynomial"), (5, 2, 0, "constant")]:
+            x = rng.standard_normal(L).astype(np.float32)
+            f = sg.SavgolFilter(n, m, d, 1.0, mode)
+            sg.set_exact(True)
+            ref = O.Filter1D(n, m, d, 1.0, mode).apply(x)
+            y = f.apply(x)                                # out of place, host
+            assert np.array_equal(y.view(np.uint32), ref.view(np.uint32)), ("oop", mode)
+            z = x.copy()
+            f.apply(z, out=z)                             # in place, host: must equal the out-of-place result
+            assert np.array_equal(z.view(np.uint32), ref.view(np.uint32)), ("in place", mode)
+            w = np.concatenate([x, np.zeros(64, np.float32)])
+            f.apply(w[:L], out=w[8:L + 8])                # partial overlap
+            assert np.array_equal(w[8:L + 8].view(np.uint32), ref.view(np.uint32)), ("overlap", mode)
+            v = f.apply_valid(x)                          # VALID through the pipeline: interior of the polynomial result
+            rv = O.Filter1D(n, m, d, 1.0, mode).apply_valid(x)
+            assert v.shape == rv.shape and np.array_equal(v.view(np.uint32), rv.view(np.uint32)), ("valid", mode)
+            sg.set_exact(False)
+            f.close()
+        # batch of rows, in place and with a pitch
+        xb = rng.standard_normal((3000, 1100)).astype(np.float32)
+        f = sg.SavgolFilter(10, 2, 1, 1.0, "reflect")
+        ref = O.Filter1D(10, 2, 1, 1.0, "reflect").apply(np.ascontiguousarray(xb[:, :1024]))
+        zb = xb.copy()
+        f.apply(zb[:, :1024], out=zb[:, :1024])
+        assert np.max(np.abs(zb[:, :1024] - ref)) <= 1e-6 * np.abs(xb).max()
+        assert np.array_equal(zb[:, 1024:], xb[:, 1024:])
+        print("ok")
+    """)
+    assert "ok" in out
+
+
+def test_mcstream_host_chunks_in_channel_blocks_equal_device_chunks():
+    out = run_child("""
+        import numpy as np, torch, savgol_b200 as sg
+        n, Cn, K = 10, 700, 1024                       # 700 channels x (1024 + 21 -> 1048 floats) = 2.9 MB -> 3 channel blocks
+        rng = np.random.default_rng(4)
+        sig = rng.standard_normal((Cn, 5 * K + 7)).astype(np.float32)
+        cuts = [0, 5, 2 * n + 1, K + 30, 2 * K + 30, 3 * K + 30, 5 * K + 7]     # incl. a chunk shorter than the window and the first fill
+        res = {}
+        for where in ("host", "device"):
+            s = sg.SavgolMCStream(Cn, n, 2, 1, 1.0)
+            got = []
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                ch = np.ascontiguousarray(sig[:, a:b])
+                if where == "device":
+                    o, k = s.push(torch.from_numpy(ch).cuda())
+                    got.append(o[:, :k].cpu().numpy())
+                else:
+                    o, k = s.push(ch)
+                    got.append(o[:, :k].copy())
+            o, k = s.flush(np.empty(1, np.float32) if where == "host" else torch.empty(1, device="cuda"))
+            got.append(o[:, :k].copy() if where == "host" else o[:, :k].cpu().numpy())
+            res[where] = np.concatenate(got, axis=1)
+            assert s.samples_received == 5 * K + 7 and s.samples_output == 5 * K + 7
+        assert res["host"].shape == sig.shape
+        assert np.array_equal(res["host"].view(np.uint32), res["device"].view(np.uint32))
+        print("ok")
+    """)
+    assert "ok" in out
+
+
+def test_mcstream_restore_reads_exactly_one_checkpoint_and_push_checks_the_pitch(capfd):
+    lib = sg.lib()
+    s = sg.SavgolMCStream(5, 4, 2, 0, 1.0)
+    x = torch.randn(5, 64, device="cuda")
+    s.push(x)
+    blob = s.save()
+    big = blob + b"\xff" * 4096                       # the caller's buffer is larger than the checkpoint
+    buf = C.create_string_buffer(big, len(big))
+    assert lib.savgol_mcstream_restore(s._h, buf, len(big)) == 0
+    o1, k1 = s.push(x)
+    s2 = sg.SavgolMCStream(5, 4, 2, 0, 1.0)
+    s2.restore(blob)
+    o2, k2 = s2.push(x)
+    assert k1 == k2 and torch.equal(o1[:, :k1], o2[:, :k2])
+    assert lib.savgol_mcstream_restore(s._h, buf, len(blob) - 1) == -1          # truncated
+    # single channel: the output row must still hold chunk_len + half_window samples (the first fill emits that many)
+    s1 = sg.SavgolMCStream(1, 4, 2, 0, 1.0)
+    xin = torch.randn(1, 32, device="cuda")
+    small = torch.empty(1, 32, device="cuda")
+    assert lib.savgol_mcstream_push(s1._h, xin.data_ptr(), 32, 32, small.data_ptr(), 32) == -1
+    assert "out_pitch" in capfd.readouterr().err
+
+
+def test_batch_multi_and_slices_on_a_device_list(oracle):
+    lib = sg.lib()
+    ndev = torch.cuda.device_count()
+    devs = [i % ndev for i in range(max(3, ndev))]
+    darr = (C.c_int * len(devs))(*devs)
+    rng = np.random.default_rng(8)
+    # (a) host batch sharded by rows
+    f = sg.SavgolFilter(16, 3, 1, 1.0, "reflect")
+    x = rng.standard_normal((301, 4096)).astype(np.float32)
+    y = np.empty_like(x)
+    assert lib.savgol_apply_batch_multi(f.handle, x.ctypes.data, y.ctypes.data, 301, 4096, 4096, 4096, darr, len(devs)) == 0
+    assert np.array_equal(bits(y), bits(f.apply(x)))
+    # (b) one long host signal partitioned along its length, all modes, exact flavour bit-identical to the oracle
+    L = (1 << 21) + 333
+    xl = rng.standard_normal(L).astype(np.float32)
+    for mode in ("periodic", "polynomial", "reflect", "constant"):
+        g = sg.SavgolFilter(32, 4, 2, 1.0, mode)
+        yl = np.empty_like(xl)
+        sg.set_exact(True)
+        assert lib.savgol_apply_batch_multi(g.handle, xl.ctypes.data, yl.ctypes.data, 1, L, L, L, darr, len(devs)) == 0
+        sg.set_exact(False)
+        assert np.array_equal(bits(yl), bits(oracle.Filter1D(32, 4, 2, 1.0, mode).apply(xl))), mode
+        g.close()
+    # (c) device-resident slices, halos read from the neighbour slices
+    for mode in ("periodic", "polynomial", "reflect"):
+        g = sg.SavgolFilter(12, 4, 1, 1.0, mode)
+        lens = [70000, 4096, 123457][:len(devs)] + [5000] * (len(devs) - 3)
+        sig = rng.standard_normal(sum(lens)).astype(np.float32)
+        ins, outs, off = [], [], 0
+        for d, ln in zip(devs, lens):
+            ins.append(torch.from_numpy(sig[off:off + ln]).to(f"cuda:{d}"))
+            outs.append(torch.empty(ln, device=f"cuda:{d}"))
+            off += ln
+        for d in set(devs):
+            torch.cuda.synchronize(d)
+        pi = (C.c_void_p * len(devs))(*[t.data_ptr() for t in ins])
+        po = (C.c_void_p * len(devs))(*[t.data_ptr() for t in outs])
+        pl = (C.c_size_t * len(devs))(*lens)
+        sg.set_exact(True)
+        assert lib.savgol_apply_slices(g.handle, pi, po, pl, darr, len(devs)) == 0
+        sg.set_exact(False)
+        got = np.concatenate([t.cpu().numpy() for t in outs])
+        assert np.array_equal(bits(got), bits(oracle.Filter1D(12, 4, 1, 1.0, mode).apply(sig))), mode
+        g.close()
+    assert lib.savgol_apply_batch_multi(f.handle, x.ctypes.data, y.ctypes.data, 301, 4096, 4096, 4096, (C.c_int * 1)(99), 1) == -1
+    f.close()
+
+
+def test_tensor_on_a_device_that_is_not_current():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    f = sg.SavgolFilter(8, 3, 0, 1.0, "reflect")
+    x = torch.randn(64, 2048, device="cuda:1")
+    with torch.cuda.device(0):
+        y = f.apply(x)
+    torch.cuda.synchronize(1)
+    ref = f.apply(x.cpu().numpy())
+    assert np.array_equal(bits(y.cpu().numpy()), bits(ref))

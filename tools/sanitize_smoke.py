@@ -52,6 +52,47 @@ imgb = torch.from_numpy(rng.random((300, 260)).astype(np.float32)).cuda()
 fb.apply_band(imgb[0:107], 0, 7, "reflect")          # top band (image border above), neighbour rows below
 fb.apply_band(imgb[93:207], 7, 7, "constant")        # interior band
 fb.apply_band(imgb[193:300], 7, 0, "constant")       # bottom band
+# bulk-tensor (TMA) paths: 1D kernels forced on for every eligible layout (full / ragged segments, halos, stream
+# chunks), 2D interior work items of aligned images (additive and rank-R kernels, half-windows 5..8)
+sg.lib().savgol_b200_set_tma(2)
+for n, m, d in [(1, 1, 0), (10, 2, 1), (16, 3, 1), (17, 4, 2), (32, 4, 2)]:
+    for mode in ("polynomial", "reflect", "periodic", "constant"):
+        f = sg.SavgolFilter(n, m, d, 1.0, mode)
+        for rows, L, pitch in [(1, 1024, 1024), (3, 2048, 2052), (2, 5000, 5000), (1, 1024 + 33, 1060), (2, 4096, 4096)]:
+            big = torch.from_numpy(rng.standard_normal((rows, pitch)).astype(np.float32)).cuda()
+            f.apply(big[:, :L])
+        x = torch.from_numpy(rng.standard_normal(3 * 4096).astype(np.float32)).cuda()
+        if n % 4 == 0:
+            f.apply_valid(x)
+        f.apply_halo(x[4096:8192], x[4096 - n:4096].clone(), x[8192:8192 + n].clone())
+        f.close()
+st = sg.SavgolMCStream(40, 10, 2, 1, 1.0)
+for K in (1024, 1024, 2048):
+    st.push(torch.from_numpy(rng.standard_normal((40, K)).astype(np.float32)).cuda(), out=torch.empty(40, K + 12, device="cuda"))
+sg.lib().savgol_b200_set_tma(1)
+for nx, o in [(5, 3), (7, 3), (8, 2), (7, 4), (6, 6)]:
+    f2 = sg.Savgol2DFilter(nx, nx, o)
+    for b in ("valid", "constant", "reflect"):
+        for shape in [(3, 700, 520), (1, 1100, 640), (2, 64, 1024)]:
+            f2.apply(torch.from_numpy(rng.random(shape).astype(np.float32)).cuda(), b)
+# host staging: pipelines, in place, VALID, stream chunks, single-process multi-GPU entry points
+hx = rng.standard_normal((37, 3000)).astype(np.float32)
+fh = sg.SavgolFilter(12, 4, 0, 1.0, "reflect")
+fh.apply(hx)
+fh.apply(hx, out=hx)
+fh.apply_valid(hx[0])
+sh = sg.SavgolMCStream(9, 6, 2, 0, 1.0)
+for K in (4, 40, 1500):
+    sh.push(rng.standard_normal((9, K)).astype(np.float32))
+import ctypes as C
+devs = (C.c_int * 3)(0, 0, 0)
+hy = np.empty_like(hx)
+assert sg.lib().savgol_apply_batch_multi(fh.handle, hx.ctypes.data, hy.ctypes.data, 37, 3000, 3000, 3000, devs, 3) == 0
+sl = [torch.from_numpy(rng.standard_normal(5000).astype(np.float32)).cuda() for _ in range(3)]
+so = [torch.empty(5000, device="cuda") for _ in range(3)]
+torch.cuda.synchronize()
+assert sg.lib().savgol_apply_slices(fh.handle, (C.c_void_p * 3)(*[t.data_ptr() for t in sl]), (C.c_void_p * 3)(*[t.data_ptr() for t in so]),
+                                    (C.c_size_t * 3)(5000, 5000, 5000), devs, 3) == 0
 sg.set_exact(True)
 f2 = sg.Savgol2DFilter(3, 2, 3)
 f2.apply(torch.from_numpy(rng.random((40, 50)).astype(np.float32)).cuda(), "reflect")
