@@ -186,6 +186,8 @@ def record_of(name, res, world, peaks, peak_kind, traffic, steps, warmup):
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": traffic, "peak_kind": peak_kind,
                      "kernel": res["kernel"], "kernel_ms": round(kern_ms, 5), "alg_bytes_per_launch": alg_bytes,
+                     "best_step_ms": round(res["best_step_ms"], 5) if res.get("best_step_ms") else None,
+                     "frac_best_step": round(alg_bytes / (res["best_step_ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"], 4) if res.get("best_step_ms") else None,
                      "fp32": {"tfma_s": round(tfma, 2), "peak": FP32_PEAK_TFMA, "frac": round(tfma / FP32_PEAK_TFMA, 4),
                               "ops_per_unit": res["fp32_ops_per_unit"],
                               "peak_kind": "FFMA lane-operations/s, tools/microbench.cu on B200 at 1965 MHz"}},
@@ -193,7 +195,7 @@ def record_of(name, res, world, peaks, peak_kind, traffic, steps, warmup):
         "gpu_launches": res["gpu_launches"], "tma_launches": res.get("tma_launches"),
         "parity": res.get("parity"),
     }
-    for k in ("sustained", "e2e", "cpu_baseline"):
+    for k in ("sustained", "strong_scaling", "e2e", "cpu_baseline"):
         if res.get(k):
             rec[k] = res[k]
     return rec

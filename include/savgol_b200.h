@@ -247,6 +247,13 @@ void savgol_b200_set_tma(int how);
 void savgol_b200_set_exact(int exact);          /* the calling host thread's flavour */
 void savgol_b200_set_exact_default(int exact);  /* process default, for threads that never chose */
 int savgol_b200_get_exact(void);
+/* In-place semantics.  Default 0: savgol_apply(f, x, x, L) returns the out-of-place result (alias safe).  1: exactly
+ * aliased savgol_apply / savgol_apply_batch calls of the calling host thread reproduce what the reference really
+ * computes in place -- its centre loop reads samples it has already overwritten (src/savgolFilter.c:763-801), a
+ * recursive result that depends on the loop order -- bit for bit, with a sequential one-thread-per-signal kernel
+ * (slow; for callers whose downstream numbers were fitted to that behaviour). */
+void savgol_b200_set_inplace_compat(int on);
+int savgol_b200_get_inplace_compat(void);
 
 /* 1D batch ---------------------------------------------------------------- */
 

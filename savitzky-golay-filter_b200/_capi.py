@@ -96,6 +96,8 @@ PROTOTYPES = {
     "savgol_b200_set_exact": (None, [C.c_int]),
     "savgol_b200_set_exact_default": (None, [C.c_int]),
     "savgol_b200_get_exact": (C.c_int, []),
+    "savgol_b200_set_inplace_compat": (None, [C.c_int]),
+    "savgol_b200_get_inplace_compat": (C.c_int, []),
     "savgol_apply_batch_multi": (C.c_int, [FP, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t,
                                            C.POINTER(C.c_int), C.c_int]),
     "savgol_apply_slices": (C.c_int, [FP, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.c_int]),
@@ -143,6 +145,8 @@ def load() -> C.CDLL:
                 "(or __graft_entry__.build()); this package has no CPU fallback")
         lib = C.CDLL(path)
         for name, (res, args) in PROTOTYPES.items():
+            if "SAVGOL_B200_LIB" in os.environ and not hasattr(lib, name):
+                continue             # an older A/B build (tools/ab.sh): symbols added since are simply absent
             fn = getattr(lib, name)  # AttributeError = header/library mismatch, fail loudly
             fn.restype = res
             fn.argtypes = args

@@ -29,6 +29,105 @@ int mode_of(const SavgolFilter* f)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Reference-compatible IN-PLACE semantics.  savgol_apply(f, x, x, L) of the reference is not alias
+// safe: its centre loop overwrites samples that later windows still read, so the "in-place" result is a recursive
+// filter whose value depends on the loop order (src/savgolFilter.c:763-801).  By default this library returns the
+// out-of-place result for aliased calls.  A caller that depends on the reference's actual in-place numbers can ask
+// for them: savgol_b200_set_inplace_compat(1) makes exactly-aliased calls run the reference's loop order -- one
+// thread per signal, sequential, the reference's 4-chain unfused arithmetic -- bit-identical to the reference.
+// The recurrence has no parallelism along a signal; a batch is parallel over its signals.
+struct CompatW { float w[sg::kMaxWs]; };
+
+__device__ __forceinline__ float compat_dot4(const float* w, int ws, const float* d, int dstep)
+{
+    // ref: src/savgolFilter.c:547-580 (dstep = +1) and :593-623 (reverse traversal, dstep = -1)
+    float s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    const int rem = ws & 3;
+    for (int k = 0; k < ws; ++k) {
+        const int c = k < rem ? k : ((k - rem) & 3);
+        s[c] = __fadd_rn(s[c], __fmul_rn(w[k], d[static_cast<long long>(k) * dstep]));
+    }
+    return __fadd_rn(__fadd_rn(s[0], s[1]), __fadd_rn(s[2], s[3]));
+}
+
+__global__ void compat_inplace_kernel(float* data, size_t rows, size_t len, size_t pitch, const CompatW W, const float* __restrict__ edge_t,
+                                      int n, int mode, float scale)
+{
+    const size_t r = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (r >= rows) return;
+    float* x = data + r * pitch;
+    const int ws = 2 * n + 1;
+    const long long L = static_cast<long long>(len);
+    for (long long j = n; j < L - n; ++j) x[j] = __fmul_rn(compat_dot4(W.w, ws, x + (j - n), 1), scale);
+    float win[sg::kMaxWs], ew[sg::kMaxWs];
+    if (mode == sg::MODE_POLY) {
+        for (int i = 0; i < n; ++i) {   // leading edge, reversed traversal from x[2n]
+            for (int k = 0; k < ws; ++k) ew[k] = edge_t[k * 32 + i];
+            x[i] = __fmul_rn(compat_dot4(ew, ws, x + (ws - 1), -1), scale);
+        }
+        for (int i = 0; i < n; ++i) {   // trailing edge
+            for (int k = 0; k < ws; ++k) ew[k] = edge_t[k * 32 + i];
+            x[L - 1 - i] = __fmul_rn(compat_dot4(ew, ws, x + (L - ws), 1), scale);
+        }
+    } else {
+        // ref: convolve_padded / get_padded_sample, src/savgolFilter.c:442-535 (64-bit indices here)
+        auto padded = [&](long long idx) -> float {
+            if (idx >= 0 && idx < L) return x[idx];
+            if (mode == sg::MODE_REFLECT) {
+                if (idx < 0) { idx = -idx - 1; if (idx >= L) idx = L - 1; }
+                else { idx = 2 * L - idx - 1; if (idx < 0) idx = 0; }
+                return x[idx];
+            }
+            if (mode == sg::MODE_PERIODIC) return x[((idx % L) + L) % L];
+            return idx < 0 ? x[0] : x[L - 1];
+        };
+        for (long long i = 0; i < n; ++i) {
+            for (int k = 0; k < ws; ++k) win[k] = padded(i - n + k);
+            x[i] = __fmul_rn(compat_dot4(W.w, ws, win, 1), scale);
+        }
+        for (long long i = L - n; i < L; ++i) {
+            for (int k = 0; k < ws; ++k) win[k] = padded(i - n + k);
+            x[i] = __fmul_rn(compat_dot4(W.w, ws, win, 1), scale);
+        }
+    }
+}
+
+thread_local int t_inplace_compat = 0;
+
+bool run_compat_inplace(const SavgolFilter* f, float* data, size_t rows, size_t len, size_t pitch, int mode)
+{
+    const MemKind k = sge::classify(data);
+    sge::DeviceGuard guard(data);
+    if (!sge::device_ready(true)) return false;
+    cudaStream_t st = sge::current_stream();
+    float* d = data;
+    size_t dpitch = pitch;
+    bool ok = true;
+    if (k != MemKind::Device) {
+        dpitch = len;
+        ok = cuda_ok(cudaMallocAsync(&d, rows * len * sizeof(float), st), "cudaMallocAsync") &&
+             cuda_ok(cudaMemcpy2DAsync(d, len * sizeof(float), data, pitch * sizeof(float), len * sizeof(float), rows, cudaMemcpyHostToDevice, st), "H2D");
+    }
+    float* temp = nullptr;
+    const float* et = ok ? sge::edge_table_device(f, st, &temp) : nullptr;
+    ok = ok && et;
+    if (ok) {
+        CompatW W;
+        std::memcpy(W.w, f->center_weights, sizeof(W.w));
+        const float scale = f->dt_scale != 0.0f ? 1.0f / f->dt_scale : 1.0f;
+        const unsigned blocks = static_cast<unsigned>((rows + 63) / 64);
+        compat_inplace_kernel<<<blocks, 64, 0, st>>>(d, rows, len, dpitch, W, et, f->config.half_window, mode, scale);
+        ok = cuda_ok(cudaGetLastError(), "compat in-place launch");
+    }
+    if (ok && k != MemKind::Device)
+        ok = cuda_ok(cudaMemcpy2DAsync(data, pitch * sizeof(float), d, len * sizeof(float), len * sizeof(float), rows, cudaMemcpyDeviceToHost, st), "D2H") &&
+             cuda_ok(cudaStreamSynchronize(st), "sync");
+    if (temp) cudaFreeAsync(temp, st);
+    if (k != MemKind::Device && d) cudaFreeAsync(d, st);
+    return ok;
+}
+
 // Dispatch on where the caller's buffers live.
 bool run1d_any(const SavgolFilter* f, const float* in, float* out, size_t rows, size_t len,
                size_t in_pitch, size_t out_pitch, int mode, bool poly_edges)
@@ -135,8 +234,13 @@ int savgol_apply_batch(const SavgolFilter* filter, const float* input, float* ou
         in_pitch = out_pitch = length;
     }
     const int mode = mode_of(filter);
+    if (t_inplace_compat && input == output && in_pitch == out_pitch)
+        return run_compat_inplace(filter, output, n_signals, length, out_pitch, mode) ? 0 : -1;
     return run1d_any(filter, input, output, n_signals, length, in_pitch, out_pitch, mode, mode == sg::MODE_POLY) ? 0 : -1;
 }
+
+void savgol_b200_set_inplace_compat(int on) { t_inplace_compat = on ? 1 : 0; }
+int savgol_b200_get_inplace_compat(void) { return t_inplace_compat; }
 
 int savgol_apply(const SavgolFilter* filter, const float* input, float* output, size_t length)
 {

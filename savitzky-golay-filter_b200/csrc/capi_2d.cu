@@ -397,18 +397,81 @@ static int component(int hx, int hy, int order, int dx, int dy, const float* in,
     return savgol2d_apply(f, in, rows, cols, stride, out, stride, boundary);
 }
 
+// The components of a gradient / Hessian share the input image and nothing else (different parities, different
+// factors).  For device images they are launched CONCURRENTLY: the first on the caller's stream, the others on side
+// streams forked from it and joined back.  One 4096^2 image gives each launch only ~1.3 work items per resident warp,
+// so two or three launches together fill the machine where one leaves SMs idle in its tail, and the second and third
+// read of the image are served from L2 (64 MiB of 126 MB) while it is still there.  (A single kernel that stages a row
+// once and accumulates 2-3 outputs needs 2-3x the accumulator registers, i.e. half the columns per lane -- the
+// measurement in profiles/ shows the concurrent launches ahead of both that and the sequential composition.)
+}  // extern "C"
+namespace {
+struct Comp { int dx, dy; float* out; };
+std::mutex g_side_mu;
+cudaStream_t g_side[sge::kMaxDevices][2] = {};
+
+int run_components(int hx, int hy, int order, const float* in, int rows, int cols, int stride, float delta_x, float delta_y,
+                   Savgol2DBoundary boundary, const Comp* comps, int n)
+{
+    static const bool seq = [] { const char* e = getenv("SAVGOL_B200_WRAP_SEQ"); return e && e[0] == '1'; }();
+    bool concurrent = n >= 2 && !seq && in && sge::classify(in) == MemKind::Device;
+    const size_t span = rows > 0 && cols > 0 ? static_cast<size_t>(rows - 1) * stride + cols : 0;
+    for (int i = 0; i < n && concurrent; ++i) {
+        concurrent = comps[i].out && sge::classify(comps[i].out) == MemKind::Device && !ranges_overlap2d(in, span, comps[i].out, span);
+        for (int j = 0; j < i && concurrent; ++j) concurrent = !ranges_overlap2d(comps[j].out, span, comps[i].out, span);
+    }
+    if (!concurrent) {
+        for (int i = 0; i < n; ++i) {
+            const int rc = component(hx, hy, order, comps[i].dx, comps[i].dy, in, rows, cols, stride, comps[i].out, delta_x, delta_y, boundary);
+            if (rc != 0) return rc;
+        }
+        return 0;
+    }
+    sge::DeviceGuard guard(in);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaStream_t user = sge::current_stream();
+    cudaStream_t side[2] = {nullptr, nullptr};
+    {
+        std::lock_guard<std::mutex> lk(g_side_mu);
+        for (int k = 0; k < n - 1; ++k) {
+            if (!g_side[dev][k] && !cuda_ok(cudaStreamCreateWithFlags(&g_side[dev][k], cudaStreamNonBlocking), "stream")) return -1;
+            side[k] = g_side[dev][k];
+        }
+    }
+    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+    if (!cuda_ok(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming), "event")) return -1;
+    cudaEventRecord(fork, user);
+    int rc = 0;
+    for (int i = 0; i < n && rc == 0; ++i) {
+        cudaStream_t st = i == 0 ? user : side[i - 1];
+        if (i > 0) cudaStreamWaitEvent(st, fork, 0);
+        savgol_b200_set_stream(st);
+        rc = component(hx, hy, order, comps[i].dx, comps[i].dy, in, rows, cols, stride, comps[i].out, delta_x, delta_y, boundary);
+        if (i > 0 && cudaEventCreateWithFlags(&join[i - 1], cudaEventDisableTiming) == cudaSuccess) {
+            cudaEventRecord(join[i - 1], st);
+            cudaStreamWaitEvent(user, join[i - 1], 0);
+        } else if (i > 0) {
+            cudaStreamSynchronize(st);
+        }
+    }
+    savgol_b200_set_stream(user);
+    cudaEventDestroy(fork);
+    for (cudaEvent_t e : join)
+        if (e) cudaEventDestroy(e);
+    return rc;
+}
+}  // namespace
+extern "C" {
+
 int savgol2d_gradient(int hx, int hy, int order, const float* input, int rows, int cols, int stride,
                       float* grad_x, float* grad_y, float delta_x, float delta_y, Savgol2DBoundary boundary)
 {
-    if (grad_x) {
-        const int rc = component(hx, hy, order, 1, 0, input, rows, cols, stride, grad_x, delta_x, delta_y, boundary);
-        if (rc != 0) return rc;
-    }
-    if (grad_y) {
-        const int rc = component(hx, hy, order, 0, 1, input, rows, cols, stride, grad_y, delta_x, delta_y, boundary);
-        if (rc != 0) return rc;
-    }
-    return 0;
+    Comp c[2];
+    int n = 0;
+    if (grad_x) c[n++] = {1, 0, grad_x};
+    if (grad_y) c[n++] = {0, 1, grad_y};
+    return run_components(hx, hy, order, input, rows, cols, stride, delta_x, delta_y, boundary, c, n);
 }
 
 int savgol2d_hessian(int hx, int hy, int order, const float* input, int rows, int cols, int stride,
@@ -418,19 +481,12 @@ int savgol2d_hessian(int hx, int hy, int order, const float* input, int rows, in
         fprintf(stderr, "savgol2d_hessian: poly_order must be >= 2\n");
         return -1;
     }
-    if (hess_xx) {
-        const int rc = component(hx, hy, order, 2, 0, input, rows, cols, stride, hess_xx, delta_x, delta_y, boundary);
-        if (rc != 0) return rc;
-    }
-    if (hess_xy) {
-        const int rc = component(hx, hy, order, 1, 1, input, rows, cols, stride, hess_xy, delta_x, delta_y, boundary);
-        if (rc != 0) return rc;
-    }
-    if (hess_yy) {
-        const int rc = component(hx, hy, order, 0, 2, input, rows, cols, stride, hess_yy, delta_x, delta_y, boundary);
-        if (rc != 0) return rc;
-    }
-    return 0;
+    Comp c[3];
+    int n = 0;
+    if (hess_xx) c[n++] = {2, 0, hess_xx};
+    if (hess_xy) c[n++] = {1, 1, hess_xy};
+    if (hess_yy) c[n++] = {0, 2, hess_yy};
+    return run_components(hx, hy, order, input, rows, cols, stride, delta_x, delta_y, boundary, c, n);
 }
 
 __global__ void add_rows_kernel(float* __restrict__ dst, const float* __restrict__ src, int rows, int cols, long long stride)

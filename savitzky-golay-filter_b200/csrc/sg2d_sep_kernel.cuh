@@ -66,6 +66,9 @@ namespace sg { extern std::atomic<unsigned long long> g_launches; }
 #ifndef SG2D_ADD_MINB
 #define SG2D_ADD_MINB 4
 #endif
+#ifndef SG2D_TMA
+#define SG2D_TMA 0   // 1: interior work items stage their rows with one bulk-tensor copy per step (experiment, see below)
+#endif
 
 namespace sg2d {
 
@@ -200,6 +203,21 @@ __device__ __noinline__ void stage_edge_pair(unsigned d, const float* r0, const 
     }
 }
 
+// Two rows of an INTERIOR strip of an image whose rows are not 16-byte aligned (odd width / stride, offset views): every
+// staged column exists, so the rows travel as lane-consecutive 4-byte copies -- each instruction still covers one
+// contiguous 128-byte run -- with no per-element boundary logic.  d = shared address of this lane's first float of the
+// first row, r0 / r1 = this lane's first source float.  Out of line: the aligned path must not pay for it.
+template <int ROWF>
+__device__ __noinline__ void stage_rows4(unsigned d, const float* r0, const float* r1, int lane)
+{
+#pragma unroll
+    for (int e0 = 0; e0 < ROWF; e0 += 32)
+        if (e0 + 32 <= ROWF || lane < ROWF - e0) {
+            cp_async4_s(d + 4 * e0, r0 + e0);
+            cp_async4_s(d + ROWF * 4 + 4 * e0, r1 + e0);
+        }
+}
+
 template <int N, int R, int RX, bool ADD>
 __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? ((N <= 6 || (N == 7 && (R == 2 || R == 3))) ? SG2D_MINB : 3) : ((N >= 15 && R >= 3) ? SG2D_WIDE_MINB : SG2D_MINB2)) sep_kernel(const __grid_constant__ typename WSel<R, ADD>::type w,
                                                                             const __grid_constant__ Args2D a, const __grid_constant__ Tma2D maps)
@@ -220,8 +238,12 @@ __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? (
     constexpr int VW = RX >= 4 ? 4 : 2;         // floats per shared load
     constexpr int NV = (WIN + VW - 1) / VW;
 
-    // TMA staging needs 128-byte aligned destinations: two rows of a step are 2 * ROWF floats apart
-    constexpr bool TMA_OK = (2 * ROWF * 4) % 128 == 0;
+    // Bulk-tensor (TMA) staging of interior work items -- compiled in with -DSG2D_TMA=1 only.  Measured on C4
+    // (profiles/r2_c4_tma_experiment.txt): 0.647 of the HBM roofline with it, 0.675 without -- the ELECT / R2UR sequence
+    // ptxas wraps around each UTMALDG plus the mbarrier wait cost more issue slots than the four LDGSTS per lane they
+    // replace, and the kernel is issue bound.  It needs 128-byte aligned destinations: two rows of a step are
+    // 2 * ROWF floats apart, so only the kernels with ROWF = 144 (half-windows 5..8) qualify.
+    constexpr bool TMA_OK = SG2D_TMA && (2 * ROWF * 4) % 128 == 0;
     __shared__ __align__(128) float s_ring[kWarps][kRing][ROWF];
     __shared__ __align__(8) unsigned long long s_mbar[kWarps][kRing / 2];
 
@@ -357,6 +379,10 @@ __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? (
                     const int nr = xb + ROWF > a.cols ? xb + ROWF - a.cols : 0;      // ... and right of it
                     stage_pads(d - 16 * lane, s0 - xb - 4 * lane, s1 - xb - 4 * lane, ROWF * 4, nl + nr, nl, xb, a.cols, a.boundary, lane);
                 }
+            } else if (x_in) {
+                stage_rows4<ROWF>(ring_lane_s - 12 * lane + slot * (ROWF * 4),   // ring_lane_s = slot 0 + 16 * lane
+                                  in + static_cast<long long>(map_index(yin0 + t, a.rows, a.boundary)) * a.in_stride + xb + lane,
+                                  in + static_cast<long long>(map_index(yin0 + t + 1, a.rows, a.boundary)) * a.in_stride + xb + lane, lane);
             } else {
                 stage_edge_pair<ROWCH, ROWF>(ring_lane_s + slot * (ROWF * 4),
                                              in + static_cast<long long>(map_index(yin0 + t, a.rows, a.boundary)) * a.in_stride,
@@ -740,7 +766,7 @@ cudaError_t launch_nr(const Args2D& a, const SepPlan& plan, cudaStream_t stream)
     Tma2D maps;
     std::memset(&maps, 0, sizeof(maps));
     aa.use_tma = 0;
-    {
+    if (SG2D_TMA) {
         constexpr int PADX = (N + 3) & ~3;
         constexpr int ROWF = TW + 2 * PADX;
         static const bool off = [] { const char* e = std::getenv("SAVGOL_B200_NO_TMA2D"); return e && e[0] == '1'; }();

@@ -179,3 +179,43 @@ def test_tensor_on_a_device_that_is_not_current():
     torch.cuda.synchronize(1)
     ref = f.apply(x.cpu().numpy())
     assert np.array_equal(bits(y.cpu().numpy()), bits(ref))
+
+
+def test_inplace_compat_mode_reproduces_the_reference_in_place_result(oracle):
+    # the reference's savgol_apply(f, x, x, L) reads samples it has already overwritten; with
+    # savgol_b200_set_inplace_compat(1) an exactly aliased call reproduces that result bit for bit (default: the
+    # alias-safe out-of-place result, which differs by ~0.1 on random data)
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    R = oracle.ref()
+    lib = sg.lib()
+    rng = np.random.default_rng(17)
+    try:
+        for n, m, d, mode in [(5, 3, 0, "polynomial"), (16, 3, 1, "reflect"), (7, 2, 2, "periodic"), (12, 4, 0, "constant"), (2, 2, 1, "polynomial")]:
+            cfg = oracle.make_config(n, m, d, 0.5, mode)
+            rf = R.savgol_create(C.byref(cfg))
+            f = sg.SavgolFilter(n, m, d, 0.5, mode)
+            for L in (2 * n + 1, 2 * n + 2, 300, 5000):
+                x = rng.standard_normal((3, L)).astype(np.float32)
+                want = x.copy()
+                for r in range(3):
+                    assert R.savgol_apply(rf, want[r].ctypes.data, want[r].ctypes.data, L) == 0
+                lib.savgol_b200_set_inplace_compat(1)
+                h = x.copy()
+                f.apply(h, out=h)                                      # host, in place
+                dv = torch.from_numpy(x.copy()).cuda()
+                f.apply(dv, out=dv)                                    # device, in place
+                one = torch.from_numpy(x[0].copy()).cuda()
+                f.apply(one, out=one)                                  # savgol_apply (single signal)
+                lib.savgol_b200_set_inplace_compat(0)
+                assert np.array_equal(bits(h), bits(want)), (n, mode, L, "host")
+                assert np.array_equal(bits(dv.cpu().numpy()), bits(want)), (n, mode, L, "device")
+                assert np.array_equal(bits(one.cpu().numpy()), bits(want[0])), (n, mode, L, "single")
+                # default semantics: the out-of-place result
+                dflt = torch.from_numpy(x.copy()).cuda()
+                f.apply(dflt, out=dflt)
+                assert torch.equal(dflt, f.apply(torch.from_numpy(x).cuda()))
+            R.savgol_destroy(rf)
+            f.close()
+    finally:
+        lib.savgol_b200_set_inplace_compat(0)

@@ -8,6 +8,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 import savgol_b200 as sg  # noqa: E402
+from tolerance import l1_gain_1d, l1_gain_2d, parity_tol  # noqa: E402
 
 MODES = ["polynomial", "reflect", "periodic", "constant"]
 
@@ -21,14 +22,6 @@ def _fast_mode():
     sg.set_exact(False)
     yield
     sg.set_exact(False)
-
-
-def _gain(o):
-    """The north_star bound 1e-6*max|x|/dt^d presumes weight rows with an L1 norm of order 1 (smoothing /
-    well-conditioned derivatives).  Interpolating filters (m close to 2n, high derivative) amplify: one ulp of
-    the result already exceeds that bound, for the reference as much as for us.  The sweep therefore scales
-    the bound by the largest L1 norm among the weight rows in use (1 for the ordinary filters)."""
-    return max(1.0, float(np.abs(o.center).sum()), float(np.abs(o.edge).sum(axis=1).max()))
 
 
 def _random_filter(rng):
@@ -61,7 +54,7 @@ def test_batch_random_sweep(oracle, seed):
         out = torch.full((rows, pitch + off), 5.0, device="cuda")
         f.apply(dx, out=out[:, off:off + L])
         got = out[:, off:off + L].cpu().numpy()
-        tol = 1e-6 * float(np.abs(x).max()) / dt ** d * _gain(o)
+        tol = parity_tol(x, 1.0 / dt ** d, l1_gain_1d(o))
         assert np.max(np.abs(got - ref)) <= tol, (seed, n, m, d, dt, mode, L, rows, pitch, off)
         assert torch.all(out[:, :off] == 5.0) and torch.all(out[:, off + L:] == 5.0)
         sg.set_exact(True)
@@ -102,7 +95,7 @@ def test_stream_random_sweep(oracle, seed):
             if exact:
                 assert np.array_equal(bits(got), bits(want)), (seed, n, m, d, chunks, C_)
             else:
-                assert np.max(np.abs(got - want)) <= 1e-6 * float(np.abs(sig).max()) / dt ** d * _gain(o), (seed, n, m, d, chunks, C_)
+                assert np.max(np.abs(got - want)) <= parity_tol(sig, 1.0 / dt ** d, l1_gain_1d(o)), (seed, n, m, d, chunks, C_)
 
 
 @pytest.mark.parametrize("seed", range(3))
@@ -127,7 +120,7 @@ def test_2d_random_sweep(oracle, seed):
         out = torch.full(x.shape, -3.0, device="cuda")
         f.apply(d_x, b, out=out)
         got = out.cpu().numpy()
-        tol = 1e-6 * float(np.abs(x).max()) * o.scale * max(1.0, float(np.abs(o.W).sum()))
+        tol = parity_tol(x, o.scale, l1_gain_2d(o))
         for i in range(images):
             ref = np.full((rows, cols), -3.0, np.float32)
             o.apply(x[i], b, ref)
