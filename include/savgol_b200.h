@@ -184,7 +184,12 @@ int savgol2d_apply_valid(const Savgol2DFilter *filter,
                          const float *input, int rows, int cols, int in_stride,
                          float *output, int out_stride);
 
-/* ref: savgol2d.h:171-174 / src/savgol2d.c:398-456 */
+/* ref: savgol2d.h:171-174 / src/savgol2d.c:398-456.
+ * Non-finite pixels: the default arithmetic evaluates the window as a sum of separable factors (rank-R or
+ * additive), so an Inf / NaN pixel contaminates the same outputs as in the reference (every output whose window
+ * holds it) -- except for rectangular windows, which run with the shorter factor zero-padded to the longer
+ * half-window: an Inf / NaN up to |hx - hy| pixels outside the true window is multiplied by 0 and yields NaN where
+ * the reference stays finite.  savgol_b200_set_exact(1) runs the literal window and has the reference's footprint. */
 int savgol2d_apply(const Savgol2DFilter *filter,
                    const float *input, int rows, int cols, int in_stride,
                    float *output, int out_stride, Savgol2DBoundary boundary);

@@ -122,8 +122,11 @@ static cudaError_t sg1d_launch_tma(EncodeTiled enc, int n, int vt, const W1D& w,
 {
     TmaMaps maps;
     const unsigned long long nin = static_cast<unsigned long long>(a.len) >> 5, nout = static_cast<unsigned long long>(a.out_len) >> 5;
+    const unsigned hl = static_cast<unsigned>(((vt == VT_STREAM ? 2 * n : n) + 31) / 32);   // GeoT<LEAD>::HL
     if (!encode_rows(enc, &maps.in_body, a.in, nin, a.rows, a.in_row_bytes, 32) ||
-        !encode_rows(enc, &maps.in_row, a.in, nin, a.rows, a.in_row_bytes, 1))
+        !encode_rows(enc, &maps.in_first, a.in, nin, a.rows, a.in_row_bytes, 33) ||
+        !encode_rows(enc, &maps.in_last, a.in, nin, a.rows, a.in_row_bytes, hl + 32) ||
+        !encode_rows(enc, &maps.in_full, a.in, nin, a.rows, a.in_row_bytes, hl + 33))
         return cudaErrorNotSupported;
     a.out_tma = nout >= 32 ? 1 : 0;
     if (a.out_tma && !encode_rows(enc, &maps.out_body, a.out, nout, a.rows, a.out_row_bytes, 32)) return cudaErrorNotSupported;

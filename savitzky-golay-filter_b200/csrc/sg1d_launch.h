@@ -17,8 +17,10 @@ struct Kernel1D {
 
 // Tensor maps of the TMA kernels (sg1d_tma.cuh): the batch seen as {32 floats, len / 32, rows}, SWIZZLE_128B.
 struct alignas(64) TmaMaps {
-    CUtensorMap in_body;   // box {32, 32, 1}: the 1024 samples under a segment's outputs
-    CUtensorMap in_row;    // box {32, 1, 1}: one 128-byte halo row
+    CUtensorMap in_full;   // box {32, HL + 33, 1}: left halo rows + the 1024 samples under a segment's outputs + right halo row
+    CUtensorMap in_first;  // box {32, 33, 1}: body + right halo row (first segment of a signal)
+    CUtensorMap in_last;   // box {32, HL + 32, 1}: left halo rows + body (last full segment)
+    CUtensorMap in_body;   // box {32, 32, 1}: a signal that is one segment
     CUtensorMap out_body;  // box {32, 32, 1}
 };
 struct Kernel1DTma {

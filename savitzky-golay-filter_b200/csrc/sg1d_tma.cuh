@@ -6,9 +6,10 @@
 // src/savgol_stream.c:224-226).  What changes is how a segment travels:
 //
 //   * LOADS.  The batch is described to the TMA unit as a 3-D tensor {32 floats, len/32, rows} with
-//     SWIZZLE_128B.  A segment (1024 outputs of one row) is one 32-row box (4 KB) plus one box per
-//     128-byte halo row on either side -- two or three `cp.async.bulk.tensor` issued by ONE lane, landing
-//     on the warp's private mbarrier -- instead of nine LDGSTS per lane with their address arithmetic.
+//     SWIZZLE_128B.  A segment (1024 outputs of one row) is ONE box: its 32 body rows (4 KB) plus the
+//     128-byte halo rows that exist on either side (four tensor maps that differ only in their box height)
+//     -- one `cp.async.bulk.tensor` issued by ONE lane, landing on the warp's private mbarrier -- instead of
+//     nine LDGSTS per lane with their address arithmetic.
 //     Halo rows that do not exist as tensor rows (first / last segment of a signal) are never touched by
 //     the TMA unit; the edge path fills them exactly as before: one element per lane, a 4-byte cp.async
 //     from the address the boundary rule designates (reflect / periodic / constant / explicit halo in a
@@ -241,14 +242,10 @@ __global__ void __launch_bounds__(kThreads, SG_MIN_BLOCKS)
         const bool lh = t > 0;                       // the halo rows exist as tensor rows of this signal
         const bool rh = (t + 1) * 32 < nrows_in;
         if (lane == 0) {
+            // ONE box per segment: body + whichever halo rows exist (four tensor maps that differ in their box height)
+            const CUtensorMap* m = lh ? (rh ? &maps.in_full : &maps.in_last) : (rh ? &maps.in_first : &maps.in_body);
             mbar_expect_tx(mbar, 4096u + (lh ? 128u * HL : 0u) + (rh ? 128u : 0u));
-            const int r = static_cast<int>(row), j0 = static_cast<int>(32 * t);
-            tma_load_3d(buf + 128 * HL, &maps.in_body, 0, j0, r, mbar);
-            if (lh) {
-#pragma unroll
-                for (int h = 0; h < HL; ++h) tma_load_3d(buf + 128 * h, &maps.in_row, 0, j0 - HL + h, r, mbar);
-            }
-            if (rh) tma_load_3d(buf + 128 * (HL + 32), &maps.in_row, 0, j0 + 32, r, mbar);
+            tma_load_3d(buf + (lh ? 0 : 128 * HL), m, 0, static_cast<int>(32 * t) - (lh ? HL : 0), static_cast<int>(row), mbar);
         }
         // edge path: the halo elements the TMA unit did not bring (true ends of the signal)
         if (!lh) {

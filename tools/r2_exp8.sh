@@ -1,0 +1,16 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+echo "== full gpu test suite"; timeout 1800 python -m pytest tests -x -q -m gpu 2>&1 | tail -6
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 300 python tools/perf_shapes2d.py 2>&1 | head -5
+echo "== default bench"
+( time timeout 800 python bench.py > gpurun_out/bench_all.json 2> gpurun_out/bench_all.err ) 2>&1 | tail -3
+tail -1 gpurun_out/bench_all.json | python -c "
+import sys,json
+d=json.loads(sys.stdin.read())
+def show(k,r): print(k, r['value'], r['ms_per_step'], r['roofline']['frac'], r['roofline'].get('frac_best_step'), r['roofline']['fp32']['frac'], 'parity', r['parity'].get('ok'), 'e2e', r.get('e2e',{}).get('value'), 'sust', (r.get('sustained') or {}).get('frac_hbm'), 'cpu', (r.get('cpu_baseline') or {}).get('value'), r['clocks']['reasons'])
+show('c2', d)
+for k,v in d['configs'].items(): show(k,v)
+"
+tail -3 gpurun_out/bench_all.err
