@@ -244,7 +244,7 @@ unsigned long long savgol_b200_launch_count(void);
  * samples, default arithmetic); SAVGOL_B200_NO_TMA=1 in the environment routes them to the cp.async kernels. */
 unsigned long long savgol_b200_tma_launch_count(void);
 /* Experiment / test switch for the above (process-wide): 0 never, 1 (default) where they measured faster
- * (half-windows up to 19, launches of >= 2048 segments), 2 wherever the data layout allows. */
+ * (half-windows up to 17, launches of >= 2048 segments), 2 wherever the data layout allows. */
 void savgol_b200_set_tma(int how);
 /* Arithmetic flavour: 0 (default) = FMA chains, within 1e-6*max|x|/dt^d of the
  * reference; 1 = "exact": the reference's own summation order with unfused

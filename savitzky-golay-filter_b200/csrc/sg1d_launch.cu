@@ -83,11 +83,12 @@ bool encode_rows(EncodeTiled enc, CUtensorMap* m, const void* base, unsigned lon
 }
 
 // The TMA kernels take contiguous fp32 rows of at least one segment whose base and pitch are 16-byte aligned.
-// Whether they are FASTER than the cp.async kernels was measured on B200 (tools/r2_sweep1d.py, profiles/):
-// yes for half-windows up to 19 (the staging / store instructions they save are issue slots the FFMA2 stream
-// can use; +2 ... +8 %), no for the wide windows that are fp32-pipe bound anyway (20 ... 32: -2 ... -6 %, except
-// 26 where the cp.async instantiation is the slow one), and no for launches of fewer than ~2048 segments, where
-// the first tensor-map fetch is exposed latency.  g_tma_enabled: 0 off, 1 this rule, 2 always (tests).
+// Whether they are FASTER than the cp.async kernels was measured on B200 (tools/r2_sweep1d.py, profiles/r2_sweep1d.txt,
+// 65,536 x 4,096): yes for half-windows up to 17 (+2 ... +10 %: 0.91 of the HBM roofline at n <= 4, 0.87 at n = 16; the
+// staging / store instructions they save are issue slots the FFMA2 stream can use), no for the wide windows that are
+// fp32-pipe bound anyway (18 ... 32: -1 ... -9 %, except 26 where the cp.async instantiation is the slow one), and no
+// for launches of fewer than ~2048 segments, where the first tensor-map fetch is exposed latency (64 segments: 13 vs
+// 8 us).  g_tma_enabled: 0 off, 1 this rule, 2 always (tests).
 bool tma_eligible(int n, int variant, const Args1D& a)
 {
     const int how = g_tma_enabled.load(std::memory_order_relaxed);
@@ -97,7 +98,7 @@ bool tma_eligible(int n, int variant, const Args1D& a)
     if (a.rows > 1 && ((a.in_row_bytes | a.out_row_bytes) & 15)) return false;
     if (a.rows >= (1LL << 31) || a.len >= (1LL << 36) || a.in_row_bytes >= (1LL << 40) || a.out_row_bytes >= (1LL << 40)) return false;
     if (how == 1) {
-        if (!(n <= 19 || n == 26)) return false;
+        if (!(n <= 17 || n == 26)) return false;
         if (((a.len + kTile - 1) / kTile) * a.rows < 2048) return false;
     }
     return true;

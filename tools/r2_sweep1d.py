@@ -33,11 +33,11 @@ def timeit(f, x, y, reps, do_flush):
 
 print("== half-window sweep, 65536 x 4096, m3 d0 reflect (d0: no zero centre weight)")
 x = torch.randn(65536, 4096, device="cuda"); y = torch.empty_like(x)
-for n in (2, 4, 6, 8, 10, 12, 14, 16, 18, 20, 22, 24, 26, 28, 30, 32):
-    f = sg.SavgolFilter(n, 3, 0, 1.0, "reflect")
+for n in range(1, 33):
+    f = sg.SavgolFilter(n, min(3, 2 * n), 0, 1.0, "reflect")
     r = []
     for on in (1, 0):
-        lib.savgol_b200_set_tma(on)
+        lib.savgol_b200_set_tma(2 if on else 0)
         r.append(timeit(f, x, y, 10, False))
     lib.savgol_b200_set_tma(1)
     print(f"n={n:2d} tma {r[0]:.4f} ms ({8*x.numel()/r[0]/1e6/6553.6:.3f})  cp.async {r[1]:.4f} ms ({8*x.numel()/r[1]/1e6/6553.6:.3f})  ratio {r[1]/r[0]:.3f}")
@@ -48,7 +48,7 @@ for rows in (16, 64, 256, 1024, 2048, 4096, 8192, 16384):
     f = sg.SavgolFilter(16, 3, 1, 1.0, "reflect")
     r = []
     for on in (1, 0):
-        lib.savgol_b200_set_tma(on)
+        lib.savgol_b200_set_tma(2 if on else 0)
         r.append(timeit(f, x, y, 10, True))
     lib.savgol_b200_set_tma(1)
     print(f"rows={rows:6d} segments={rows*4:6d} tma {r[0]*1e3:.1f} us  cp.async {r[1]*1e3:.1f} us")
@@ -58,7 +58,7 @@ for L, n in ((1_000_000, 12), (1 << 24, 12), (1 << 28, 32), (1 << 28, 16)):
     f = sg.SavgolFilter(n, 4, 0, 1.0, "polynomial")
     r = []
     for on in (1, 0):
-        lib.savgol_b200_set_tma(on)
+        lib.savgol_b200_set_tma(2 if on else 0)
         r.append(timeit(f, x, y, 10, L < (1 << 26)))
     lib.savgol_b200_set_tma(1)
     print(f"L={L} n={n} tma {r[0]*1e3:.1f} us  cp.async {r[1]*1e3:.1f} us")
