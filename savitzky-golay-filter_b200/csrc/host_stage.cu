@@ -150,6 +150,11 @@ bool run1d_host_range(Pipeline& P, const SavgolFilter* f, const float* x, size_t
     const size_t padl = (n + 3) & ~static_cast<size_t>(3);
     const size_t piece = chunk_floats();
     if (b <= a) return true;
+    if ((a != 0 && a < n) || (b != L && b + n > L) || b > L) {   // a cut must leave n real samples on its far side (or be a true end)
+        fprintf(stderr, "savgol_b200: internal: host range [%lu, %lu) of %lu samples is closer than half_window to an end\n",
+                static_cast<unsigned long>(a), static_cast<unsigned long>(b), static_cast<unsigned long>(L));
+        return false;
+    }
     // slot layout: [padl-n slack | n left halo | piece (+ up to one window) | n right halo]
     if (!P.ensure(padl + piece + 2 * sg::kMaxWs + n, piece + sg::kMaxWs)) return false;
 

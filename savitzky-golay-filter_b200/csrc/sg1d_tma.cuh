@@ -228,6 +228,8 @@ __global__ void __launch_bounds__(kThreads, SG_MIN_BLOCKS)
         fence_proxy_async();
     }
     __syncwarp();
+    const bool has_poly = (a.edge_lead | a.edge_trail) != 0;   // launch-uniform
+    const bool has_state = a.state_out != nullptr;
     unsigned par_cur = 0, par_nxt = 0;    // phase parity each buffer's mbarrier completes next
     bool tma_cur = false, tma_nxt = false;
 
@@ -292,8 +294,9 @@ __global__ void __launch_bounds__(kThreads, SG_MIN_BLOCKS)
         cp_async_commit();
 
         // polynomial edge outputs of this segment, one lane per output.  ref: src/savgolFilter.c:769-784
-        const bool lead_seg = a.edge_lead && o0 < N;
-        const bool trail_seg = a.edge_trail && (o0 + kSeg > len - N);
+        // (one launch-uniform flag keeps the polynomial-edge / stream-state bookkeeping off the common path)
+        const bool lead_seg = has_poly && a.edge_lead && o0 < N;
+        const bool trail_seg = has_poly && a.edge_trail && (o0 + kSeg > len - N);
         if (lead_seg && lane < N) {
             const float s = dot_ordered<WS, ARITH_FAST>([&](int k) { return a.edge_t[k * 32 + lane]; },
                                                         [&](int k) { return ld_sample(xrow, 4, 2 * N - k); });
@@ -324,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, SG_MIN_BLOCKS)
         }
 
         // stream: the last state_w samples of [lead pad | x] become the next chunk's history
-        if (a.state_out != nullptr && o0 + kSeg >= len) {
+        if (has_state && o0 + kSeg >= len) {
             const long long first = len - a.state_w;
             const bool staged = first >= o0 - LEAD;
             for (int i = lane; i < a.state_w; i += 32) {

@@ -82,7 +82,10 @@ using sg::cp_async_wait;
 constexpr int kU = SG2D_KU;         // rows per statically indexed block
 constexpr int kRing = 8;      // staged rows per warp
 constexpr int kAhead = 6;     // prefetch distance in rows (kRing >= kAhead + 2)
-constexpr int kBandMax = 512; // output rows per work item (upper bound; the launcher shrinks it for small batches)
+#ifndef SG2D_BAND
+#define SG2D_BAND 512
+#endif
+constexpr int kBandMax = SG2D_BAND; // output rows per work item (upper bound; the launcher shrinks it for small batches)
 constexpr int kWarps = 4;
 
 template <int R>
