@@ -161,7 +161,7 @@ void plan_separable(int nx, int ny, int order, const double* coef, const float* 
     // one-variable functions and both "other" factors are constant 1 -- box sums for the kernel
     // (sg2d_add.cu).  The constant is split so that v vanishes at the window ends (two taps less).
     static const bool no_additive = [] { const char* e = std::getenv("SAVGOL_B200_NO_ADDITIVE"); return e && e[0] == '1'; }();
-    if (rank == 2 && px == 1 && py == 1 && nx == ny && nx <= 8 && !no_additive) {
+    if (rank == 2 && px == 1 && py == 1 && nx == ny && nx <= 16 && !no_additive) {
         const double wcc = W[static_cast<size_t>(ny) * ww + nx];
         double dev = 0.0;
         for (int y = 0; y < wh; ++y)

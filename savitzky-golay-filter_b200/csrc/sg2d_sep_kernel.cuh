@@ -105,9 +105,9 @@ struct alignas(64) Tma2D {
 // Additive surface W(y,x) = u(x) + v(y) (sg2d_add.cu).  Row weights as pairs for the sample-broadcast FFMA2 form:
 // sample x[c+i] is tap i of column c and tap i-1 of column c+1.
 struct AddW {
-    float2 pu[2 * 8 + 1];   // pu[j] = (u[j], u[j-1]), j = 1..2n  (u[0..2n] = u(-n..n) * scale)
+    float2 pu[2 * 16 + 1];  // pu[j] = (u[j], u[j-1]), j = 1..2n  (u[0..2n] = u(-n..n) * scale)
     float u_first, u_last;  // u[0], u[2n]: the two half pairs at the window ends
-    float col[2 * 8 + 1];   // v[0..2n] * scale, v[0] = v[2n] = 0
+    float col[2 * 16 + 1];  // v[0..2n] * scale, v[0] = v[2n] = 0
 };
 template <int R, bool ADD> struct WSel { using type = SepW<R>; };
 template <int R> struct WSel<R, true> { using type = AddW; };
@@ -225,7 +225,7 @@ template <int N, int R, int RX, bool ADD>
 __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? ((N <= 6 || (N == 7 && (R == 2 || R == 3))) ? SG2D_MINB : 3) : ((N >= 15 && R >= 3) ? SG2D_WIDE_MINB : SG2D_MINB2)) sep_kernel(const __grid_constant__ typename WSel<R, ADD>::type w,
                                                                             const __grid_constant__ Args2D a, const __grid_constant__ Tma2D maps)
 {
-    static_assert(!ADD || (R == 1 && RX == 4 && N <= 8), "additive variant: one weight set, 4 columns per lane, static ring");
+    static_assert(!ADD || (R == 1 && (RX == 4 || RX == 2) && N <= 16), "additive variant: one weight set, static ring");
     constexpr int TW = 32 * RX;                 // output columns per strip
     constexpr int PADX = (N + 3) & ~3;          // staged row starts PADX columns left of the strip (16 B aligned)
     constexpr int DX = PADX - N;
@@ -479,8 +479,13 @@ __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? (
             const float* rowp = ring_lane + (t & (kRing - 1)) * ROWF + (RX - 4) * lane;
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
-                const float4 q = *reinterpret_cast<const float4*>(rowp + 4 * v);
-                xs[4 * v] = q.x; xs[4 * v + 1] = q.y; xs[4 * v + 2] = q.z; xs[4 * v + 3] = q.w;
+                if constexpr (VW == 4) {
+                    const float4 q = *reinterpret_cast<const float4*>(rowp + 4 * v);
+                    xs[4 * v] = q.x; xs[4 * v + 1] = q.y; xs[4 * v + 2] = q.z; xs[4 * v + 3] = q.w;
+                } else {
+                    const float2 q = *reinterpret_cast<const float2*>(rowp + 2 * v);
+                    xs[2 * v] = q.x; xs[2 * v + 1] = q.y;
+                }
             }
             constexpr int C0 = DX + N;   // window index of the lane's first column
             // A: sample-broadcast form (as in the 1D kernel) -- xs[c + i] is tap i of column c and tap i - 1 of

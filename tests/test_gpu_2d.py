@@ -22,7 +22,9 @@ def _fast_mode():
 
 
 CASES = [(1, 1, 1, 0, 0), (2, 2, 2, 0, 0), (2, 2, 2, 1, 0), (2, 1, 2, 0, 1), (3, 4, 4, 1, 1), (7, 7, 3, 0, 0), (7, 7, 3, 2, 0),
-         (5, 3, 6, 2, 2), (16, 16, 6, 0, 0), (4, 4, 3, 0, 0), (8, 8, 2, 0, 2), (12, 12, 5, 1, 0)]
+         (5, 3, 6, 2, 2), (16, 16, 6, 0, 0), (4, 4, 3, 0, 0), (8, 8, 2, 0, 2), (12, 12, 5, 1, 0),
+         # additive surfaces (order 2/3 smoothing): 4 columns per lane up to 17x17, 2 columns per lane above
+         (1, 1, 2, 0, 0), (3, 3, 3, 0, 0), (8, 8, 3, 0, 0), (9, 9, 3, 0, 0), (12, 12, 2, 0, 0), (16, 16, 3, 0, 0)]
 
 
 @pytest.mark.parametrize("nx,ny,order,dx,dy", CASES)

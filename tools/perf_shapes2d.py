@@ -6,7 +6,7 @@ import torch
 import savgol_b200 as sg
 
 for (nx, ny, order, images, rows, cols) in [(7, 7, 3, 16, 4096, 4096), (7, 7, 3, 16, 4096, 4095), (7, 7, 3, 1, 4096, 4096), (7, 7, 3, 64, 1024, 1024),
-                                             (2, 2, 2, 16, 4096, 4096), (4, 4, 4, 16, 4096, 4096), (7, 3, 3, 16, 4096, 4096), (9, 9, 3, 16, 4096, 4096), (10, 10, 5, 16, 4096, 4096), (12, 12, 3, 16, 4096, 4096),
+                                             (2, 2, 2, 16, 4096, 4096), (4, 4, 4, 16, 4096, 4096), (7, 3, 3, 16, 4096, 4096), (9, 9, 3, 16, 4096, 4096), (10, 10, 5, 16, 4096, 4096), (12, 12, 3, 16, 4096, 4096), (16, 16, 3, 16, 4096, 4096), (8, 8, 3, 16, 4096, 4096),
                                              (16, 16, 6, 16, 4096, 4096), (8, 8, 6, 16, 4096, 4096), (8, 8, 4, 16, 4096, 4096), (7, 7, 5, 16, 4096, 4096),
                                              (6, 6, 6, 16, 4096, 4096), (4, 4, 6, 16, 4096, 4096)]:
     f = sg.Savgol2DFilter(nx, ny, order)
