@@ -70,10 +70,10 @@ st = sg.SavgolMCStream(40, 10, 2, 1, 1.0)
 for K in (1024, 1024, 2048):
     st.push(torch.from_numpy(rng.standard_normal((40, K)).astype(np.float32)).cuda(), out=torch.empty(40, K + 12, device="cuda"))
 sg.lib().savgol_b200_set_tma(1)
-for nx, o in [(5, 3), (7, 3), (8, 2), (7, 4), (6, 6)]:
+for nx, o in [(5, 3), (7, 3), (8, 2), (7, 4), (6, 6), (9, 3), (16, 2)]:
     f2 = sg.Savgol2DFilter(nx, nx, o)
     for b in ("valid", "constant", "reflect"):
-        for shape in [(3, 700, 520), (1, 1100, 640), (2, 64, 1024)]:
+        for shape in [(3, 700, 520), (1, 1100, 640), (2, 64, 1024), (1, 200, 517)]:   # 517: rows not 16-byte aligned, interior strips
             f2.apply(torch.from_numpy(rng.random(shape).astype(np.float32)).cuda(), b)
 # host staging: pipelines, in place, VALID, stream chunks, single-process multi-GPU entry points
 hx = rng.standard_normal((37, 3000)).astype(np.float32)
