@@ -244,3 +244,28 @@ def test_2d_fast_path_covers_the_configuration_space():
     assert len(rejected) <= total // 100, rejected[:20]
     assert worst <= 4e-7, worst
     assert set(ranks) <= {0, 1, 2, 3, 4}
+
+
+def test_2d_additive_plans():
+    # host-only: which filters the planner hands to the additive kernel (sg2d_add.cu): exactly the rank-2 surfaces
+    # W(y,x) = u(x) + v(y) with a square window -- every order-2/3 smoothing filter (and the even/even derivatives where
+    # they are rank 2) -- reproduced by u + v to within the same acceptance bound as the factorisations
+    import ctypes as C
+    lib = sg.lib()
+    for n in range(1, 17):
+        for order in (2, 3):
+            if (2 * n + 1) ** 2 < (order + 1) * (order + 2) // 2:
+                continue                       # fewer window points than polynomial terms (3x3, order 3)
+            f = sg.Savgol2DFilter(n, n, order)
+            r, e = C.c_int(), C.c_float()
+            assert lib.savgol2d_b200_plan(f.handle, C.byref(r), C.byref(e)) == 0
+            assert lib.savgol2d_b200_plan_kind(f.handle) == 2 and r.value == 2 and e.value <= 4e-7, (n, order, r.value, e.value)
+            # the planner's claim, checked here from the public weight table: W - (row 0 + column 0 - corner) == 0
+            W = f.weights.astype(np.float64)
+            assert np.max(np.abs(W - (W[n:n + 1, :] + W[:, n:n + 1] - W[n, n]))) <= 2e-7 * np.abs(W).max() + 1e-9
+            f.close()
+    for args, kind in (((7, 7, 1), 1), ((7, 7, 0), 1), ((7, 7, 4), 1), ((7, 5, 3), 1), ((7, 7, 3, 1, 0), 1), ((7, 7, 3, 1, 1), 1)):
+        f = sg.Savgol2DFilter(*args)
+        assert lib.savgol2d_b200_plan_kind(f.handle) == kind, args
+        f.close()
+    assert lib.savgol2d_b200_plan_kind(None) == -1
