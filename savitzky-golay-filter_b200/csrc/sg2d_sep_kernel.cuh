@@ -80,8 +80,12 @@ using sg::cp_async_commit;
 using sg::cp_async_wait;
 
 constexpr int kU = SG2D_KU;         // rows per statically indexed block
-constexpr int kRing = 8;      // staged rows per warp
-constexpr int kAhead = 6;     // prefetch distance in rows (kRing >= kAhead + 2)
+#ifndef SG2D_QUAD
+#define SG2D_QUAD 1   // 1: rows are staged four at a time (every other step); 0: two at a time (every step)
+#endif
+constexpr int kStage = SG2D_QUAD ? 4 : 2;       // rows per staging call / cp.async group
+constexpr int kRing = SG2D_QUAD ? 16 : 8;       // staged rows per warp
+constexpr int kAhead = SG2D_QUAD ? 8 : 6;       // prefetch distance in rows (kRing >= kAhead + kStage)
 #ifndef SG2D_BAND
 #define SG2D_BAND 512
 #endif
@@ -393,16 +397,35 @@ __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? (
                                              xb, a.cols, a.boundary, lane);
             }
         };
-        // rows t, t+1 have landed: this lane's cp.async copies, or the step's bulk-tensor copy
-        auto wait_pair = [&](int t) {
+        // Staging schedule: at every kStage-th row the group that holds rows t .. t+kStage-1 must have landed (this lane's
+        // cp.async copies -- or the bulk-tensor copies --, then everybody else's), and the rows kAhead ahead are issued
+        // into the slots of rows that are fully consumed.  With kStage = 4 the wait / barrier / address bookkeeping runs on
+        // every other step only.
+        auto wait_rows = [&](int t) {
             if (item_tma) {
-                const int q = (t & (kRing - 1)) >> 1;
-                sg::mbar_wait(mbar0 + 8 * q, (par_bits >> q) & 1u);
-                par_bits ^= 1u << q;
+#pragma unroll
+                for (int u = 0; u < kStage; u += 2)
+                    if (t + u < steps2) {
+                        const int q = ((t + u) & (kRing - 1)) >> 1;
+                        sg::mbar_wait(mbar0 + 8 * q, (par_bits >> q) & 1u);
+                        par_bits ^= 1u << q;
+                    }
             } else {
-                cp_async_wait<kAhead / 2 - 1>();
+                cp_async_wait<kAhead / kStage - 1>();
             }
-            __syncwarp();   // ... and everybody else's; rows t-2, t-1 are fully consumed
+            __syncwarp();   // ... and everybody else's; the rows before t are fully consumed
+        };
+        auto stage_rows = [&](int t) {
+#pragma unroll
+            for (int u = 0; u < kStage; u += 2)
+                if (t + u < steps2) stage_pair(t + u);
+            cp_async_commit();
+        };
+        auto advance = [&](int t) {
+            if ((t & (kStage - 1)) == 0) {
+                wait_rows(t);
+                stage_rows(t + kAhead);
+            }
         };
         // store side, hoisted: this lane's columns, whether they lie inside the stored region and
         // whether a vector store is legal; the row pointer advances by the output pitch per emitted row
@@ -418,10 +441,7 @@ __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? (
         // is padded with one extra (boundary-mapped) row whose contributions are never emitted.
         __syncwarp();  // the previous item's last reads of the ring are done
 #pragma unroll 1
-        for (int t = 0; t < kAhead; t += 2) {
-            if (t < steps2) stage_pair(t);
-            cp_async_commit();
-        }
+        for (int t = 0; t < kAhead; t += kStage) stage_rows(t);
 
         // acc[jp][i]: partially accumulated output rows of the column pair (2jp, 2jp+1) of this lane.
         //   RING:  output row y (band-local, y = t - wy) lives in slot (y mod NA), NA = 2n+2; the main loop
@@ -549,9 +569,7 @@ __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? (
             int phase = 0;
 #pragma unroll 1
             for (int t = 0; t < steps2; t += 2) {
-                wait_pair(t);
-                if (t + kAhead < steps2) stage_pair(t + kAhead);
-                cp_async_commit();
+                advance(t);
 
                 float2 A0[RX / 2], B0[RX / 2], A1[RX / 2], B1[RX / 2];
                 row_pass_add(t, A0, B0);
@@ -610,9 +628,7 @@ __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? (
             int phase = 0;
 #pragma unroll 1
             for (int t = 0; t < steps2; t += 2) {
-                wait_pair(t);
-                if (t + kAhead < steps2) stage_pair(t + kAhead);   // into the slots of rows t-2, t-1
-                cp_async_commit();
+                advance(t);
 
                 float2 h0[R][RX / 2], h1[R][RX / 2];
                 row_pass(t, h0);
@@ -661,9 +677,7 @@ __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? (
                 for (int u = 0; u < kU; u += 2) {
                     const int t = tb * kU + u;
                     if (t < steps2) {
-                        wait_pair(t);
-                        if (t + kAhead < steps2) stage_pair(t + kAhead);   // into the slots of rows t-2, t-1
-                        cp_async_commit();
+                        advance(t);
 
                         float2 h0[R][RX / 2], h1[R][RX / 2];
                         row_pass(t, h0);
