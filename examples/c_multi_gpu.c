@@ -4,6 +4,7 @@
  *   (2) savgol_apply_batch_multi : ONE long host signal partitioned along its length (config 3 shape)
  *   (3) savgol_apply_slices      : one periodic signal resident on the GPUs as consecutive slices; each
  *                                  device reads its 2 x half_window halo samples from its ring neighbours' memory
+ *   (4) savgol2d_apply_batch_multi: a host batch of images sharded over the devices (BASELINE config 4, scaled down)
  * Each result is compared bit for bit with the single-GPU call of the same library in its `exact` flavour
  * (which is itself bit-identical to the reference C code) and within tolerance in the default flavour.
  *
@@ -126,6 +127,22 @@ int main(int argc, char **argv)
         }
         free(x); free(y); free(z);
         savgol_destroy(f);
+    }
+    /* (4) a host batch of images sharded over the devices */
+    {
+        Savgol2DConfig cfg = {7, 7, 3, 0, 0, 1.0f, 1.0f};
+        Savgol2DFilter *f = savgol2d_create(&cfg);
+        const int rows = 300, cols = 520;
+        const size_t images = 13, px = (size_t)rows * cols;
+        float *x = malloc(images * px * sizeof(float)), *y = malloc(images * px * sizeof(float)), *z = malloc(images * px * sizeof(float));
+        for (size_t i = 0; i < images * px; ++i) x[i] = frand(&seed);
+        int ok = f != NULL;
+        ok = ok && savgol2d_apply_batch(f, x, rows, cols, cols, px, z, cols, px, images, SAVGOL2D_BOUNDARY_CONSTANT) == 0;
+        ok = ok && savgol2d_apply_batch_multi(f, x, rows, cols, cols, px, y, cols, px, images, SAVGOL2D_BOUNDARY_CONSTANT, devices, nd) == 0;
+        ok = ok && memcmp(y, z, images * px * sizeof(float)) == 0;
+        check(ok, "image batch sharded over the device list == single-device batch (bit for bit)");
+        free(x); free(y); free(z);
+        savgol2d_destroy(f);
     }
     printf("%s\n", failures ? "FAILED" : "all multi-GPU checks passed");
     return failures ? 1 : 0;

@@ -305,6 +305,14 @@ int savgol_apply_batch_multi(const SavgolFilter *filter, const float *input, flo
 int savgol_apply_slices(const SavgolFilter *filter, const float *const *in_slices, float *const *out_slices,
                         const size_t *lengths, const int *devices, int n_slices);
 
+/* savgol2d_apply_batch_multi: HOST images sharded over the devices in contiguous blocks (independent images: no
+ * communication), one staging pipeline per device.  Arguments and result as savgol2d_apply_batch. */
+int savgol2d_apply_batch_multi(const Savgol2DFilter *filter,
+                               const float *input, int rows, int cols, int in_stride, size_t in_image_pitch,
+                               float *output, int out_stride, size_t out_image_pitch,
+                               size_t n_images, Savgol2DBoundary boundary,
+                               const int *devices, int n_devices);
+
 /* Device memory for callers without CUDA headers (examples/c_multi_gpu.c). */
 int savgol_b200_device_count(void);
 void *savgol_b200_alloc(int device, size_t bytes);

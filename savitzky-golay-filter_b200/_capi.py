@@ -100,6 +100,8 @@ PROTOTYPES = {
     "savgol_b200_get_inplace_compat": (C.c_int, []),
     "savgol_apply_batch_multi": (C.c_int, [FP, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t,
                                            C.POINTER(C.c_int), C.c_int]),
+    "savgol2d_apply_batch_multi": (C.c_int, [F2, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_int,
+                                             C.POINTER(C.c_int), C.c_int]),
     "savgol_apply_slices": (C.c_int, [FP, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.c_int]),
     "savgol_b200_device_count": (C.c_int, []),
     "savgol_b200_alloc": (C.c_void_p, [C.c_int, C.c_size_t]),

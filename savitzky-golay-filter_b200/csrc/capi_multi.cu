@@ -166,6 +166,38 @@ int savgol_apply_batch_multi(const SavgolFilter* filter, const float* input, flo
     return 0;
 }
 
+int savgol2d_apply_batch_multi(const Savgol2DFilter* filter, const float* input, int rows, int cols, int in_stride, size_t in_image_pitch,
+                               float* output, int out_stride, size_t out_image_pitch, size_t n_images, Savgol2DBoundary boundary,
+                               const int* devices, int n_devices)
+{
+    if (!filter || !input || !output) return -1;
+    if (n_images == 0) return 0;
+    if (!devices_ok(devices, n_devices, "savgol2d_apply_batch_multi")) return -1;
+    if (sge::classify(input) == MemKind::Device || sge::classify(output) == MemKind::Device) {
+        fprintf(stderr, "savgol2d_apply_batch_multi: host buffers only (device buffers belong to one GPU: savgol2d_apply_batch)\n");
+        return -1;
+    }
+    // independent images: contiguous blocks per device, one host thread (and one staging pipeline) per device
+    const size_t nd = std::min<size_t>(static_cast<size_t>(n_devices), n_images);
+    const int exact = sge::exact_mode();
+    std::vector<int> rc(nd, 0);
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < nd; ++i) {
+        th.emplace_back([&, i] {
+            if (!cuda_ok(cudaSetDevice(devices[i]), "cudaSetDevice")) { rc[i] = -1; return; }
+            savgol_b200_set_exact(exact);   // the caller's flavour
+            const size_t i0 = n_images * i / nd, i1 = n_images * (i + 1) / nd;
+            if (i1 > i0)
+                rc[i] = savgol2d_apply_batch(filter, input + i0 * in_image_pitch, rows, cols, in_stride, in_image_pitch,
+                                             output + i0 * out_image_pitch, out_stride, out_image_pitch, i1 - i0, boundary);
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int v : rc)
+        if (v != 0) return -1;
+    return 0;
+}
+
 int savgol_apply_slices(const SavgolFilter* filter, const float* const* in_slices, float* const* out_slices, const size_t* lengths,
                         const int* devices, int n_slices)
 {

@@ -54,4 +54,4 @@ def test_multi_gpu_api_from_plain_c():
         pytest.skip("drop-in binaries not built")
     p = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-1500:] + p.stderr[-1500:]
-    assert p.stdout.count("[PASS]") == 4 and "[FAIL]" not in p.stdout, p.stdout
+    assert p.stdout.count("[PASS]") == 5 and "[FAIL]" not in p.stdout, p.stdout

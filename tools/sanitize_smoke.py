@@ -88,6 +88,10 @@ import ctypes as C
 devs = (C.c_int * 3)(0, 0, 0)
 hy = np.empty_like(hx)
 assert sg.lib().savgol_apply_batch_multi(fh.handle, hx.ctypes.data, hy.ctypes.data, 37, 3000, 3000, 3000, devs, 3) == 0
+imgs = rng.random((5, 120, 260)).astype(np.float32)
+imgo = np.empty_like(imgs)
+f7 = sg.Savgol2DFilter(7, 7, 3)
+assert sg.lib().savgol2d_apply_batch_multi(f7.handle, imgs.ctypes.data, 120, 260, 260, 120 * 260, imgo.ctypes.data, 260, 120 * 260, 5, 1, devs, 3) == 0
 sl = [torch.from_numpy(rng.standard_normal(5000).astype(np.float32)).cuda() for _ in range(3)]
 so = [torch.empty(5000, device="cuda") for _ in range(3)]
 torch.cuda.synchronize()
