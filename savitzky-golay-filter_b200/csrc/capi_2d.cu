@@ -156,26 +156,22 @@ int apply2d_any(const Savgol2DFilter* f, const float* in, int rows, int cols, in
         }
     }
     const size_t img_in = static_cast<size_t>(rows) * cols, img_out = static_cast<size_t>(orows) * ocols;
+    P.begin(in, out);
     if (!P.ensure(img_in, img_out)) return -1;
     for (size_t i = 0; i < n_images; ++i) {
         const int s = static_cast<int>(i % sge::Pipeline::kSlots);
-        if (i >= sge::Pipeline::kSlots) cudaStreamWaitEvent(P.s_in, P.e_out[s], 0);
-        if (!cuda_ok(cudaMemcpy2DAsync(P.d_in[s], static_cast<size_t>(cols) * sizeof(float), in + i * ipitch,
-                                       static_cast<size_t>(is) * sizeof(float), static_cast<size_t>(cols) * sizeof(float), rows,
-                                       cudaMemcpyHostToDevice, P.s_in), "H2D")) return -1;
+        if (!P.reuse(s)) return -1;
+        if (!P.h2d(s, P.d_in[s], cols, in + i * ipitch, is, cols, rows)) return -1;
         cudaEventRecord(P.e_in[s], P.s_in);
         cudaStreamWaitEvent(P.s_k, P.e_in[s], 0);
         if (i >= sge::Pipeline::kSlots) cudaStreamWaitEvent(P.s_k, P.e_out[s], 0);
         if (!run2d_device(f, P.d_in[s], rows, cols, cols, 0, P.d_out[s], ocols, 0, 1, boundary, P.s_k)) return -1;
         cudaEventRecord(P.e_k[s], P.s_k);
         cudaStreamWaitEvent(P.s_out, P.e_k[s], 0);
-        if (!cuda_ok(cudaMemcpy2DAsync(out + i * opitch, static_cast<size_t>(os) * sizeof(float), P.d_out[s],
-                                       static_cast<size_t>(ocols) * sizeof(float), static_cast<size_t>(ocols) * sizeof(float), orows,
-                                       cudaMemcpyDeviceToHost, P.s_out), "D2H")) return -1;
+        if (!P.d2h(s, out + i * opitch, os, P.d_out[s], ocols, ocols, orows)) return -1;
         cudaEventRecord(P.e_out[s], P.s_out);
     }
-    return cuda_ok(cudaStreamSynchronize(P.s_out), "sync") && cuda_ok(cudaStreamSynchronize(P.s_k), "sync") &&
-           cuda_ok(cudaStreamSynchronize(P.s_in), "sync") ? 0 : -1;
+    return P.finish() ? 0 : -1;
 }
 
 }  // namespace

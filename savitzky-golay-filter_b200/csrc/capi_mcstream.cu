@@ -232,7 +232,7 @@ long long savgol_mcstream_push(SavgolMCStream* s, const float* input, size_t in_
     sge::Pipeline& P = *lease;
     const size_t K = chunk_len;
     const size_t opitch = (K + static_cast<size_t>(s->ws) + 3) & ~static_cast<size_t>(3);   // 16-byte aligned rows
-    const size_t cb = std::max<size_t>(1, std::min(s->channels, sge::chunk_floats() / opitch));
+    const size_t cb = std::max<size_t>(1, std::min(s->channels, P.begin(input, output) / opitch));
     if (!P.ensure(cb * K, cb * opitch)) return -1;
     cudaEvent_t prior = nullptr;
     if (cudaEventCreateWithFlags(&prior, cudaEventDisableTiming) == cudaSuccess) {
@@ -245,9 +245,8 @@ long long savgol_mcstream_push(SavgolMCStream* s, const float* input, size_t in_
     for (size_t b = 0; c0 < s->channels; ++b, c0 += cb) {
         const int sl = static_cast<int>(b % sge::Pipeline::kSlots);
         const size_t nc = std::min(cb, s->channels - c0);
-        if (b >= sge::Pipeline::kSlots && !cuda_ok(cudaStreamWaitEvent(P.s_in, P.e_out[sl], 0), "wait")) return -1;
-        if (!cuda_ok(cudaMemcpy2DAsync(P.d_in[sl], K * sizeof(float), input + c0 * in_pitch, in_pitch * sizeof(float), K * sizeof(float), nc,
-                                       cudaMemcpyHostToDevice, P.s_in), "H2D")) return -1;
+        if (!P.reuse(sl)) return -1;
+        if (!P.h2d(sl, P.d_in[sl], K, input + c0 * in_pitch, in_pitch, K, nc)) return -1;
         cudaEventRecord(P.e_in[sl], P.s_in);
         cudaStreamWaitEvent(P.s_k, P.e_in[sl], 0);
         if (b >= sge::Pipeline::kSlots) cudaStreamWaitEvent(P.s_k, P.e_out[sl], 0);
@@ -256,13 +255,10 @@ long long savgol_mcstream_push(SavgolMCStream* s, const float* input, size_t in_
         produced = k;
         cudaEventRecord(P.e_k[sl], P.s_k);
         cudaStreamWaitEvent(P.s_out, P.e_k[sl], 0);
-        if (k > 0 && !cuda_ok(cudaMemcpy2DAsync(output + c0 * out_pitch, out_pitch * sizeof(float), P.d_out[sl], opitch * sizeof(float),
-                                                static_cast<size_t>(k) * sizeof(float), nc, cudaMemcpyDeviceToHost, P.s_out), "D2H")) return -1;
+        if (k > 0 && !P.d2h(sl, output + c0 * out_pitch, out_pitch, P.d_out[sl], opitch, static_cast<size_t>(k), nc)) return -1;
         cudaEventRecord(P.e_out[sl], P.s_out);
     }
-    const bool ok = cuda_ok(cudaStreamSynchronize(P.s_out), "sync") && cuda_ok(cudaStreamSynchronize(P.s_k), "sync") &&
-                    cuda_ok(cudaStreamSynchronize(P.s_in), "sync");
-    if (!ok) return -1;
+    if (!P.finish()) return -1;
     advance(s, K, produced);
     return produced;
 }

@@ -63,8 +63,9 @@ bool run1d_device(const Problem1D& p, cudaStream_t stream);
 const float* edge_table_device(const SavgolFilter* f, cudaStream_t stream, float** temp);
 
 // Host-buffer staging.  Three device slots form a ring; H2D, kernel and D2H of consecutive
-// chunks overlap on three streams.  Pinned host memory is DMA'd directly; pageable memory goes
-// through the driver's staging (cudaMemcpyAsync degrades gracefully to a synchronous copy).
+// chunks overlap on three streams.  Pinned host memory is DMA'd directly.  Pageable memory (malloc, numpy)
+// cannot be: the driver would stage it synchronously at ~7 GB/s, so it is moved through pinned bounce
+// buffers by a few host threads (copy_threads()), which overlaps with the DMA of the neighbouring chunks.
 // A pipeline belongs to ONE device and is used by ONE host-pointer call at a time (PipeLease).
 struct Pipeline {
     static constexpr int kSlots = 3;
@@ -74,11 +75,33 @@ struct Pipeline {
     float* d_in[kSlots] = {};
     float* d_out[kSlots] = {};
     size_t cap_in = 0, cap_out = 0;  // floats per slot
+    // pinned bounce buffers, one per slot and direction, allocated when a call brings pageable memory
+    float* h_in[kSlots] = {};
+    float* h_out[kSlots] = {};
+    size_t cap_h_in = 0, cap_h_out = 0;
+    bool bounce_in = false, bounce_out = false;   // this call's input / output is pageable
+    struct Pending { float* dst; size_t dst_pitch, width, rows; unsigned long long seq; };
+    Pending pend[kSlots] = {};                    // D2H landed (or landing) in h_out[slot], still to be handed to the caller
+    unsigned long long seq = 0;
 
-    // Streams / events on first use, slots grown on demand.  The current device must be `dev`.
+    // Start of a host-pointer call: classifies its buffers.  Returns the staging chunk in floats.
+    size_t begin(const void* in, const void* out);
+    // Streams / events on first use, slots (and bounce buffers, when this call needs them) grown on demand.
+    // The current device must be `dev`.
     bool ensure(size_t need_in, size_t need_out);
+    // Before slot `s` is refilled: hands a pending bounced output to the caller and orders s_in behind the slot's D2H.
+    bool reuse(int s);
+    // Copies (floats: pitches, width) on s_in / s_out.  The caller records e_in[s] / e_out[s] afterwards.
+    bool h2d(int s, float* dev_dst, size_t dev_pitch, const float* src, size_t src_pitch, size_t width, size_t rows);
+    bool d2h(int s, float* dst, size_t dst_pitch, const float* dev_src, size_t dev_pitch, size_t width, size_t rows);
+    // End of the call: pending outputs handed over (oldest first), all three streams drained.
+    bool finish();
     void release();
 };
+
+// Multi-threaded host copy of `rows` rows of `width` BYTES (pitches in bytes); used by the bounce path.
+void host_copy2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width, size_t rows);
+int copy_threads();
 
 // Lease of an idle pipeline of the CURRENT device for the duration of one host-pointer call.  Concurrent
 // calls (several host threads, several devices) each get their own pipeline: nothing serialises them
@@ -120,6 +143,6 @@ bool run1d_host_range(Pipeline& P, const SavgolFilter* f, const float* x, size_t
 // is longer than a staging chunk).  Uses a pipeline of the current device.
 bool run1d_host(const SavgolFilter* f, const float* in, float* out, size_t rows, size_t len, size_t in_pitch,
                 size_t out_pitch, int mode, bool poly_edges, int arith);
-size_t chunk_floats();
+size_t chunk_floats(bool bounce = false);
 
 }  // namespace sge

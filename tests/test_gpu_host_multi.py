@@ -219,3 +219,99 @@ def test_inplace_compat_mode_reproduces_the_reference_in_place_result(oracle):
             f.close()
     finally:
         lib.savgol_b200_set_inplace_compat(0)
+
+
+def test_pageable_host_buffers_take_the_bounce_path_and_match_pinned_bit_for_bit():
+    """malloc / numpy memory cannot be DMA'd: it crosses pinned bounce buffers filled by the host copy pool
+    (host_stage.cu).  Results must not depend on the kind of host memory, on mixing kinds, or on how many host
+    threads are staging at once."""
+    import threading
+
+    lib = sg.lib()
+    rng = np.random.default_rng(11)
+    rows, L = 8192 + 3, 4096                                  # 128 MiB: nine 16 MiB bounce chunks, ragged last one
+    x = rng.standard_normal((rows, L), dtype=np.float32)
+    f = sg.SavgolFilter(16, 3, 1, 1.0, "reflect")
+    xp = torch.empty(rows, L, dtype=torch.float32, pin_memory=True)
+    xp.copy_(torch.from_numpy(x))
+    yp = torch.empty(rows, L, dtype=torch.float32, pin_memory=True)
+    assert lib.savgol_apply_batch(f.handle, xp.data_ptr(), yp.data_ptr(), rows, L, L, L) == 0
+    want = yp.numpy().copy()
+    yd = f.apply(torch.from_numpy(x).cuda()).cpu().numpy()    # device path
+    assert np.array_equal(bits(yd), bits(want))
+
+    y = np.full_like(x, np.nan)
+    assert lib.savgol_apply_batch(f.handle, x.ctypes.data, y.ctypes.data, rows, L, L, L) == 0          # pageable -> pageable
+    assert np.array_equal(bits(y), bits(want))
+    y[:] = np.nan
+    assert lib.savgol_apply_batch(f.handle, xp.data_ptr(), y.ctypes.data, rows, L, L, L) == 0          # pinned -> pageable
+    assert np.array_equal(bits(y), bits(want))
+    yp.zero_()
+    assert lib.savgol_apply_batch(f.handle, x.ctypes.data, yp.data_ptr(), rows, L, L, L) == 0          # pageable -> pinned
+    assert np.array_equal(bits(yp.numpy()), bits(want))
+    z = x.copy()
+    assert lib.savgol_apply_batch(f.handle, z.ctypes.data, z.ctypes.data, rows, L, L, L) == 0          # in place
+    assert np.array_equal(bits(z), bits(want))
+    # pitched rows: only the first 4000 samples of each row are filtered, the tail must stay untouched
+    z = x.copy()
+    f2 = sg.SavgolFilter(9, 2, 0, 1.0, "polynomial")
+    assert lib.savgol_apply_batch(f2.handle, z.ctypes.data, z.ctypes.data, rows, 4000, L, L) == 0
+    ref = f2.apply(torch.from_numpy(np.ascontiguousarray(x[:, :4000])).cuda()).cpu().numpy()
+    assert np.array_equal(bits(z[:, :4000]), bits(ref)) and np.array_equal(z[:, 4000:], x[:, 4000:])
+
+    # one long pageable signal (pieces with halos), in place too
+    xs = rng.standard_normal(40 * (1 << 20) + 777, dtype=np.float32)    # 160 MiB: eleven pieces
+    fs = sg.SavgolFilter(12, 4, 2, 0.5, "periodic")
+    ws = fs.apply(torch.from_numpy(xs).cuda()).cpu().numpy()
+    ys = fs.apply(xs)
+    assert np.array_equal(bits(ys), bits(ws))
+    zs = xs.copy()
+    fs.apply(zs, out=zs)
+    assert np.array_equal(bits(zs), bits(ws))
+
+    # four host threads staging pageable batches at once share the copy pool
+    parts = np.array_split(np.arange(rows), 4)
+    outs = [np.empty((len(p), L), np.float32) for p in parts]
+    ins = [np.ascontiguousarray(x[p]) for p in parts]
+    rc = [None] * 4
+
+    def work(i):
+        rc[i] = lib.savgol_apply_batch(f.handle, ins[i].ctypes.data, outs[i].ctypes.data, len(parts[i]), L, L, L)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert rc == [0, 0, 0, 0]
+    assert np.array_equal(bits(np.concatenate(outs)), bits(want))
+
+    # 2D images and the multichannel stream: pageable == pinned
+    g = sg.Savgol2DFilter(3, 3, 3)
+    imgs = rng.standard_normal((5, 1024, 1536), dtype=np.float32)
+    ip = torch.empty(imgs.shape, dtype=torch.float32, pin_memory=True)
+    ip.copy_(torch.from_numpy(imgs))
+    op = torch.empty(imgs.shape, dtype=torch.float32, pin_memory=True)
+    g.apply(ip, "reflect", out=op)
+    o = g.apply(imgs, "reflect")
+    assert np.array_equal(bits(o), bits(op.numpy()))
+    o2 = imgs.copy()
+    g.apply(o2, "reflect", out=o2)                            # in place, one image per slot
+    assert np.array_equal(bits(o2), bits(o))
+
+    ch, K = 3000, 2048                                        # 24 MiB per push: two channel blocks
+    got = []
+    for pinned in (False, True):
+        st = sg.SavgolMCStream(ch, 8, 3)
+        acc = []
+        for k in range(2):
+            blk = np.ascontiguousarray(x[:ch, k * K:(k + 1) * K])
+            if pinned:
+                t = torch.empty(ch, K, dtype=torch.float32, pin_memory=True)
+                t.copy_(torch.from_numpy(blk))
+                blk = t
+            out, cnt = st.push(blk)
+            acc.append(np.asarray(out[:, :cnt]).copy())
+        out, cnt = st.flush(blk)
+        acc.append(np.asarray(out[:, :cnt]).copy())
+        got.append(np.concatenate(acc, axis=1))
+        st.close()
+    assert got[0].shape == (ch, 2 * K) and np.array_equal(bits(got[0]), bits(got[1]))
