@@ -374,10 +374,9 @@ Savgol2DFilter* cached_filter(const WrapKey& key, Make make)
 }  // namespace
 extern "C" {
 
-static int component(int hx, int hy, int order, int dx, int dy, const float* in, int rows, int cols, int stride, float* out,
-                     float delta_x, float delta_y, Savgol2DBoundary boundary)
+static Savgol2DFilter* component_filter(int hx, int hy, int order, int dx, int dy, float delta_x, float delta_y)
 {
-    Savgol2DFilter* f = cached_filter(WrapKey{hx, hy, order, dx, dy, delta_x, delta_y}, [&]() -> Savgol2DFilter* {
+    return cached_filter(WrapKey{hx, hy, order, dx, dy, delta_x, delta_y}, [&]() -> Savgol2DFilter* {
         Savgol2DConfig cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.half_window_x = static_cast<uint8_t>(hx);
@@ -389,17 +388,26 @@ static int component(int hx, int hy, int order, int dx, int dy, const float* in,
         cfg.delta_y = delta_y;
         return savgol2d_create(&cfg);
     });
+}
+
+static int component(int hx, int hy, int order, int dx, int dy, const float* in, int rows, int cols, int stride, float* out,
+                     float delta_x, float delta_y, Savgol2DBoundary boundary)
+{
+    Savgol2DFilter* f = component_filter(hx, hy, order, dx, dy, delta_x, delta_y);
     if (!f) return -1;
     return savgol2d_apply(f, in, rows, cols, stride, out, stride, boundary);
 }
 
 // The components of a gradient / Hessian share the input image and nothing else (different parities, different
-// factors).  For device images they are launched CONCURRENTLY: the first on the caller's stream, the others on side
-// streams forked from it and joined back.  One 4096^2 image gives each launch only ~1.3 work items per resident warp,
-// so two or three launches together fill the machine where one leaves SMs idle in its tail, and the second and third
-// read of the image are served from L2 (64 MiB of 126 MB) while it is still there.  (A single kernel that stages a row
-// once and accumulates 2-3 outputs needs 2-3x the accumulator registers, i.e. half the columns per lane -- the
-// measurement in profiles/ shows the concurrent launches ahead of both that and the sequential composition.)
+// factors).  For device images, in order of preference:
+//   1. ONE launch of the multi-output kernel (sg2d_multi.cu): the image is staged once, every component has its own
+//      accumulator ring -- half-windows <= 4, full-size boundaries, default arithmetic;
+//   2. CONCURRENT per-component launches: the first on the caller's stream, the others on side streams forked from
+//      it and joined back (one 4096^2 image gives a launch only ~1.3 work items per resident warp, so two or three
+//      launches together fill the machine, and the later reads of the image are served from L2);
+//   3. the sequential composition of the reference (host images, aliased buffers, the exact flavour).
+// Measured on B200 (tools/r2_wrappers.py, profiles/r2_wrappers.txt).  SAVGOL_B200_WRAP_SEQ=1 forces 3,
+// SAVGOL_B200_WRAP_FUSED=0 skips 1.
 }  // extern "C"
 namespace {
 struct Comp { int dx, dy; float* out; };
@@ -416,6 +424,36 @@ int run_components(int hx, int hy, int order, const float* in, int rows, int col
         concurrent = comps[i].out && sge::classify(comps[i].out) == MemKind::Device && !ranges_overlap2d(in, span, comps[i].out, span);
         for (int j = 0; j < i && concurrent; ++j) concurrent = !ranges_overlap2d(comps[j].out, span, comps[i].out, span);
     }
+    // HOST images (what a caller of the reference passes): upload the image ONCE, run the device path below -- one
+    // multi-output launch where it exists -- and fetch every component, instead of one upload per component.
+    // Buffers that overlap keep the reference's component-by-component order.
+    if (n >= 2 && !seq && in && rows > 0 && cols > 0 && stride >= cols && sge::classify(in) != MemKind::Device) {
+        bool plain = true;
+        for (int i = 0; i < n && plain; ++i) {
+            plain = comps[i].out && sge::classify(comps[i].out) != MemKind::Device && !ranges_overlap2d(in, span, comps[i].out, span);
+            for (int j = 0; j < i && plain; ++j) plain = !ranges_overlap2d(comps[j].out, span, comps[i].out, span);
+        }
+        if (plain && sge::device_ready(true)) {
+            cudaStream_t st = sge::current_stream();
+            const size_t img = static_cast<size_t>(rows) * cols;
+            float* d = nullptr;
+            if (!cuda_ok(cudaMallocAsync(&d, (n + 1) * img * sizeof(float), st), "cudaMallocAsync(wrapper images)")) return -1;
+            int rc = cuda_ok(cudaMemcpy2DAsync(d, static_cast<size_t>(cols) * sizeof(float), in, static_cast<size_t>(stride) * sizeof(float),
+                                               static_cast<size_t>(cols) * sizeof(float), rows, cudaMemcpyHostToDevice, st), "H2D") ? 0 : -1;
+            Comp dc[3];
+            for (int i = 0; i < n; ++i) dc[i] = Comp{comps[i].dx, comps[i].dy, d + (i + 1) * img};
+            if (rc == 0) rc = run_components(hx, hy, order, d, rows, cols, cols, delta_x, delta_y, boundary, dc, n);
+            // VALID defines the interior only, and the reference leaves the border of the output untouched
+            const int oy = boundary == SAVGOL2D_BOUNDARY_VALID ? hy : 0, ox = boundary == SAVGOL2D_BOUNDARY_VALID ? hx : 0;
+            for (int i = 0; i < n && rc == 0; ++i)
+                rc = cuda_ok(cudaMemcpy2DAsync(comps[i].out + static_cast<size_t>(oy) * stride + ox, static_cast<size_t>(stride) * sizeof(float),
+                                               dc[i].out + static_cast<size_t>(oy) * cols + ox, static_cast<size_t>(cols) * sizeof(float),
+                                               static_cast<size_t>(cols - 2 * ox) * sizeof(float), rows - 2 * oy, cudaMemcpyDeviceToHost, st), "D2H") ? 0 : -1;
+            if (!cuda_ok(cudaStreamSynchronize(st), "sync")) rc = -1;
+            cudaFreeAsync(d, st);
+            return rc;
+        }
+    }
     if (!concurrent) {
         for (int i = 0; i < n; ++i) {
             const int rc = component(hx, hy, order, comps[i].dx, comps[i].dy, in, rows, cols, stride, comps[i].out, delta_x, delta_y, boundary);
@@ -424,6 +462,34 @@ int run_components(int hx, int hy, int order, const float* in, int rows, int col
         return 0;
     }
     sge::DeviceGuard guard(in);
+    static const bool fused = [] { const char* e = getenv("SAVGOL_B200_WRAP_FUSED"); return !(e && e[0] == '0'); }();
+    if (fused && !sge::exact_mode() && boundary != SAVGOL2D_BOUNDARY_VALID && rows > 0 && cols > 0 && sge::device_ready(true)) {
+        const Filter2DImpl* fi[3] = {nullptr, nullptr, nullptr};
+        const sg2d::SepPlan* plans[3] = {nullptr, nullptr, nullptr};
+        float scales[3] = {0.f, 0.f, 0.f};
+        bool have = true;
+        for (int i = 0; i < n && have; ++i) {
+            Savgol2DFilter* f = component_filter(hx, hy, order, comps[i].dx, comps[i].dy, delta_x, delta_y);
+            if (!f) return -1;
+            fi[i] = live2d(f);
+            have = fi[i] != nullptr;
+            if (have) { plans[i] = &fi[i]->plan; scales[i] = f->scale; }
+        }
+        if (have) {
+            sg2d::Args2D a{};
+            a.in = in;
+            a.out = comps[0].out; a.out1 = comps[1].out; a.out2 = n > 2 ? comps[2].out : nullptr;
+            a.rows = rows; a.cols = cols;
+            a.nx = hx; a.ny = hy;
+            a.in_stride = a.out_stride = stride;
+            a.n_images = 1;
+            a.boundary = boundary == SAVGOL2D_BOUNDARY_REFLECT ? sg2d::B_REFLECT : sg2d::B_CONSTANT;
+            a.scale = 1.0f;   // per component, folded into the column factors
+            a.out_rows = rows; a.out_cols = cols;
+            if (sg2d::multi_supported(a, plans, n))
+                return cuda_ok(sg2d::launch_multi(a, plans, scales, n, sge::current_stream()), "sg2d multi-output launch") ? 0 : -1;
+        }
+    }
     int dev = 0;
     cudaGetDevice(&dev);
     cudaStream_t user = sge::current_stream();

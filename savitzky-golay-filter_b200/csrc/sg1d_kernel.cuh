@@ -111,21 +111,43 @@ __device__ __noinline__ void stage_unaligned(float* d, const char* s, int lo, in
         if (32 * i >= lo && 32 * i < hi) cp_async4(d + 36 * i, s + 128 * i);
 }
 
-// Lane-interleaved scalar stores of a parked segment (ragged last segment, misaligned or strided rows):
-// output f = lane + 32 i is parked at float position lane + 36 i; it is stored when 32 i < lim.
-static __device__ __noinline__ void store_scalar(const float* srcf, char* dst, long long stride, int lim)
+// Lane-interleaved scalar stores of a parked segment (misaligned or strided rows): output f = lane + 32 i is
+// parked at float position lane + 36 i; it is stored when lo <= 32 i < lim (bounds relative to the lane).
+static __device__ __noinline__ void store_scalar(const float* srcf, char* dst, long long stride, int lo, int lim)
 {
     if (stride == 4) {
         float* d = reinterpret_cast<float*>(dst);
 #pragma unroll
         for (int i = 0; i < kR; ++i)
-            if (32 * i < lim) d[32 * i] = srcf[36 * i];
+            if (32 * i >= lo && 32 * i < lim) d[32 * i] = srcf[36 * i];
     } else {
         const long long step = 32 * stride;
 #pragma unroll 4
         for (int i = 0; i < kR; ++i) {
-            if (32 * i < lim) *reinterpret_cast<float*>(dst) = srcf[36 * i];
+            if (32 * i >= lo && 32 * i < lim) *reinterpret_cast<float*>(dst) = srcf[36 * i];
             dst += step;
+        }
+    }
+}
+
+// A parked segment whose chunks are 16-byte aligned in global memory but whose ends are cut (the first segment of
+// a phase-shifted row starts before output 0, the last one is ragged): whole chunks as 16-byte stores, the cut
+// chunks element by element.  Chunk lane + 32 i holds outputs 128 i .. 128 i + 3 relative to the lane's first;
+// [lo, hi) are the outputs that exist, in the same coordinates.
+static __device__ __noinline__ void store_cut(const float4* src /* buf + lane + (lane >> 3) */, float* dst, int lo, int hi)
+{
+#pragma unroll
+    for (int i = 0; i < kR / 4; ++i) {
+        const int e = 128 * i;
+        if (e + 4 <= lo || e >= hi) continue;
+        const float4 v = src[36 * i];
+        if (e >= lo && e + 4 <= hi) {
+            st_cs_f4(dst + e, v);
+        } else {
+            if (e >= lo && e < hi) dst[e] = v.x;
+            if (e + 1 >= lo && e + 1 < hi) dst[e + 1] = v.y;
+            if (e + 2 >= lo && e + 2 < hi) dst[e + 2] = v.z;
+            if (e + 3 >= lo && e + 3 < hi) dst[e + 3] = v.w;
         }
     }
 }
@@ -141,14 +163,14 @@ static __device__ __noinline__ void store_scalar(const float* srcf, char* dst, l
 template <int LEAD, int N>
 __device__ __forceinline__ void stage_segment(float4* dst0 /* buf + lane + (lane >> 3) */, float4* buf, const Args1D& a,
                                               const char* xrow, long long row, long long o0, int left /* min(len-o0, big) */,
-                                              bool rows_aligned, int lane)
+                                              int cap /* outputs this segment may produce: kSeg, or kSeg + kTail */, bool rows_aligned, int lane)
 {
     constexpr int PAD = Geo<LEAD>::PAD;
     constexpr int DELTA = Geo<LEAD>::DELTA;
     // segment-local 32-bit bookkeeping: chunk c covers x indices o0 - PAD + 4c .. +3
-    const int nout = left < kSeg ? left : kSeg;
+    const int nout = left < cap ? left : cap;
     const int nch = (nout + 2 * N + DELTA + 3) >> 2;          // chunks the compute loop may touch
-    const int c_lo = o0 == 0 ? PAD / 4 : 0;                    // first chunk made of four existing samples
+    const int c_lo = o0 <= 0 ? (PAD - static_cast<int>(o0) + 3) >> 2 : 0;   // first chunk made of four existing samples (o0 < 0: phase-shifted row)
     const int c_all = (left + PAD) >> 2;                       // chunks that end inside the row
     const int c_hi = c_all < nch ? c_all : nch;
     const char* src0 = xrow + (o0 - PAD) * a.in_stride;        // only dereferenced inside [c_lo, c_hi)
@@ -174,7 +196,7 @@ __device__ __forceinline__ void stage_segment(float4* dst0 /* buf + lane + (lane
             }
         }
     } else if (a.in_stride == 4) {
-        constexpr int NE = (4 * ((kSeg + 2 * N + DELTA + 3) / 4) + 31) / 32;
+        constexpr int NE = (4 * ((kSeg + kTail + 2 * N + DELTA + 3) / 4) + 31) / 32;
         stage_unaligned<NE>(reinterpret_cast<float*>(buf) + lane, src0 + 4 * lane, 4 * c_lo - lane, 4 * c_hi - lane);
     } else {
         const long long st = a.in_stride;
@@ -188,10 +210,12 @@ __device__ __forceinline__ void stage_segment(float4* dst0 /* buf + lane + (lane
             }
         }
     }
-    const int nl = 4 * c_lo, nrest = nl + 4 * (nch - c_hi);
+    // (elements more than LEAD samples before the row belong to outputs that do not exist: phase-shifted first segment)
+    const int el0 = o0 < 0 ? static_cast<int>(-o0) + DELTA : 0;
+    const int nl = 4 * c_lo - el0, nrest = nl + 4 * (nch - c_hi);
 #pragma unroll 1
     for (int q = lane; q < nrest; q += 32) {
-        const int el = q < nl ? q : 4 * c_hi + (q - nl);  // element index inside the segment buffer
+        const int el = q < nl ? el0 + q : 4 * c_hi + (q - nl);  // element index inside the segment buffer
         const int c = el >> 2;
         float* d = reinterpret_cast<float*>(buf + c + (c >> 3)) + (el & 3);
         const float* sp = sample_address<LEAD, N>(a, xrow, row, o0 - PAD + el);
@@ -307,7 +331,7 @@ __device__ __forceinline__ void compute_exact(const float4* __restrict__ sb, con
 
 template <int N, int DELTA>
 struct Smem1D {
-    static constexpr int kSegChunks = (kSeg + 2 * N + DELTA + 3) / 4;
+    static constexpr int kSegChunks = (kSeg + kTail + 2 * N + DELTA + 3) / 4;
     static constexpr int kSegPhys = kSegChunks + (kSegChunks >> 3) + 1;
 };
 
@@ -344,11 +368,22 @@ __global__ void __launch_bounds__(kThreads, SG_MIN_BLOCKS) sg1d_kernel(const __g
     float4* buf_nxt = s_buf[warp][1];  // buffer the next segment is prefetched into
     const int lane_chunk = lane + (lane >> 3);
 
-    long long o0 = static_cast<long long>(t) * kSeg;
+    // Contiguous rows that are not 16-byte aligned (odd length or pitch, offset views) are cut on a per-row
+    // phase instead: segment t starts at output t*kSeg - sh with sh = (address of x[0] / 4) mod 32, so every
+    // segment starts on a 128-byte line of global memory: staging (and, when the output row has the same phase,
+    // the stores) runs the aligned path and every warp-wide copy covers exactly four lines, as for aligned rows.
+    // The first segment then begins before output 0; those outputs are computed from whatever is staged and never
+    // stored.  a.phase is set by the launcher, which also counts the segments per row for the worst phase.
     const char* xrow = a.in + row * a.in_row_bytes;
-    if (seg < nseg) {
+    auto row_phase = [&](const char* r) -> long long { return a.phase ? static_cast<long long>((reinterpret_cast<uintptr_t>(r) >> 2) & (kPhase - 1)) : 0; };
+    long long o0 = static_cast<long long>(t) * kSeg - row_phase(xrow);
+    // a.tail: rows end with up to kTail outputs behind their last segment (launcher: a nearly empty extra segment
+    // would cost a full pass of the warp); that segment stages the extra samples and each lane adds one output.
+    const int tail_cap = a.tail ? kSeg + kTail : kSeg;
+    if (seg < nseg && o0 < len) {
         const long long l64 = len - o0;
-        stage_segment<LEAD, N>(buf_cur + lane_chunk, buf_cur, a, xrow, row, o0, static_cast<int>(l64 < kBig ? l64 : kBig), rows_aligned, lane);
+        stage_segment<LEAD, N>(buf_cur + lane_chunk, buf_cur, a, xrow, row, o0, static_cast<int>(l64 < kBig ? l64 : kBig),
+                               t + 1 == spr ? tail_cap : kSeg, rows_aligned, lane);
     }
     cp_async_commit();
 
@@ -357,19 +392,23 @@ __global__ void __launch_bounds__(kThreads, SG_MIN_BLOCKS) sg1d_kernel(const __g
         unsigned nt = t + step_t;
         long long nrow = row + step_r;
         if (nt >= spr) { nt -= spr; ++nrow; }
-        const long long no0 = static_cast<long long>(nt) * kSeg;
         const char* nxrow = a.in + nrow * a.in_row_bytes;
+        const long long no0 = static_cast<long long>(nt) * kSeg - row_phase(nxrow);
         if (seg + stride < nseg) {
             const long long l64 = len - no0;
-            stage_segment<LEAD, N>(buf_nxt + lane_chunk, buf_nxt, a, nxrow, nrow, no0,
-                                   static_cast<int>(l64 < kBig ? l64 : kBig), rows_aligned, lane);
+            if (l64 > 0)   // (a phase-shifted row may not reach into its last segment)
+                stage_segment<LEAD, N>(buf_nxt + lane_chunk, buf_nxt, a, nxrow, nrow, no0,
+                                       static_cast<int>(l64 < kBig ? l64 : kBig), nt + 1 == spr ? tail_cap : kSeg, rows_aligned, lane);
         }
         cp_async_commit();
+        const bool has_tail = a.tail && t + 1 == spr;
+        const int seg_cap = has_tail ? kSeg + kTail : kSeg;
+        if (o0 < len) {
 
         // polynomial edge outputs that fall into this segment (global reads, independent of the
         // staged data): one lane per output.  ref: src/savgolFilter.c:769-784
         const bool lead_seg = a.edge_lead && o0 < N;
-        const bool trail_seg = a.edge_trail && (o0 + kSeg > len - N);
+        const bool trail_seg = a.edge_trail && (o0 + seg_cap > len - N);
         if (lead_seg && lane < N) {
             // out[e] = scale * sum_k E[e][k] * x[2n-k]   (reversed traversal, ref :593-623)
             const float s = dot_ordered<WS, ARITH>([&](int k) { return a.edge_t[k * 32 + lane]; },
@@ -397,7 +436,7 @@ __global__ void __launch_bounds__(kThreads, SG_MIN_BLOCKS) sg1d_kernel(const __g
 #pragma unroll
             for (int j = 0; j < kR; ++j) {
                 const long long oj = o + j;
-                if (lead_seg && oj < N) out[j] = s_edge[warp][oj];
+                if (lead_seg && oj < N) { if (oj >= 0) out[j] = s_edge[warp][oj]; }
                 else if (trail_seg && oj >= len - N && oj < len) out[j] = s_edge[warp][kMaxN + (len - 1 - oj)];
             }
         }
@@ -405,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, SG_MIN_BLOCKS) sg1d_kernel(const __g
         // stream: hand the last state_w samples of [lead pad | x] to the next chunk
         // (read back from the staged segment whenever it holds them: a global re-read would put a
         // full L2 round trip on every segment's critical path)
-        if (a.state_out != nullptr && o0 + kSeg >= len) {
+        if (a.state_out != nullptr && o0 + seg_cap >= len) {
             constexpr int PAD = Geo<LEAD>::PAD;
             const long long first = len - a.state_w;         // x index of the oldest carried sample
             const bool staged = first >= o0 - PAD;
@@ -435,15 +474,49 @@ __global__ void __launch_bounds__(kThreads, SG_MIN_BLOCKS) sg1d_kernel(const __g
         __syncwarp();
         char* orow = a.out + row * a.out_row_bytes;
         const long long remain = a.out_len - o0;  // outputs of this segment that may be stored
-        if (a.out_stride == 4 && remain >= kSeg && ((reinterpret_cast<uintptr_t>(orow) + static_cast<uintptr_t>(o0 * 4)) & 15) == 0) {
+        const bool out_vec = a.out_stride == 4 && ((reinterpret_cast<uintptr_t>(orow) + static_cast<uintptr_t>(o0 * 4)) & 15) == 0;
+        if (out_vec && remain >= kSeg) {
             float* dst = reinterpret_cast<float*>(orow) + o0 + 4 * lane;
             const float4* src = buf_cur + lane + (lane >> 3);
+            // (phase-shifted first segment: outputs before 0 do not exist; they lie in the first chunks only, kPhase <= 128)
+            const int lo = o0 < 0 ? static_cast<int>(-o0) - 4 * lane : 0;   // (o0 exceeds 32 bits on long signals)
+            if (lo <= 0) {
+                st_cs_f4(dst, src[0]);
+            } else if (lo < 4) {
+                const float4 v = src[0];
+                if (lo <= 1) dst[1] = v.y;
+                if (lo <= 2) dst[2] = v.z;
+                dst[3] = v.w;
+            }
 #pragma unroll
-            for (int i = 0; i < kR / 4; ++i) st_cs_f4(dst + 128 * i, src[36 * i]);  // chunk lane + 32 i
+            for (int i = 1; i < kR / 4; ++i) st_cs_f4(dst + 128 * i, src[36 * i]);  // chunk lane + 32 i
         } else {
             const int lim = remain < kSeg ? static_cast<int>(remain) : kSeg;
-            store_scalar(reinterpret_cast<const float*>(buf_cur) + lane, orow + (o0 + lane) * a.out_stride, a.out_stride, lim - lane);
+            const int lo = o0 < 0 ? static_cast<int>(-o0) : 0;
+            if (out_vec) store_cut(buf_cur + lane + (lane >> 3), reinterpret_cast<float*>(orow) + o0 + 4 * lane, lo - 4 * lane, lim - 4 * lane);
+            else store_scalar(reinterpret_cast<const float*>(buf_cur) + lane, orow + (o0 + lane) * a.out_stride, a.out_stride, lo - lane, lim - lane);
         }
+        if (has_tail) {
+            // one more output per lane, o0 + kSeg + lane, from the samples staged behind the segment (they lie past
+            // the parked outputs).  Same operation order as compute_fast / the exact flavours: bit-identical to what
+            // a further segment would have produced.
+            const long long ot = o0 + kSeg + lane;
+            if (ot < a.out_len) {
+                const float* bf = reinterpret_cast<const float*>(buf_cur);
+                auto xs = [&](int k) { const int pos = kSeg + lane + k + DELTA; return bf[pos + 4 * (pos >> 5)]; };
+                float v;
+                if constexpr (ARITH == ARITH_FAST) {
+                    v = fmaf(W.ws_first, xs(0), 0.0f);
+#pragma unroll 4
+                    for (int k = 1; k < WS; ++k) v = fmaf(W.pw[k].x, xs(k), v);
+                } else {
+                    v = __fmul_rn(dot_ordered<WS, ARITH>([&](int k) { return W.w[k]; }, xs), a.scale);
+                }
+                if (trail_seg && ot >= len - N) v = s_edge[warp][kMaxN + (len - 1 - ot)];
+                *reinterpret_cast<float*>(orow + ot * a.out_stride) = v;
+            }
+        }
+        }  // o0 < len
         __syncwarp();  // all lanes are done with buf_cur and s_edge[warp] before the refill
         row = nrow; o0 = no0; xrow = nxrow; t = nt;
         float4* const tmp = buf_cur; buf_cur = buf_nxt; buf_nxt = tmp;

@@ -14,6 +14,8 @@ SG_DECL(0) SG_DECL(1) SG_DECL(2) SG_DECL(3) SG_DECL(4) SG_DECL(5) SG_DECL(6) SG_
 
 std::atomic<unsigned long long> g_launches{0};
 std::atomic<unsigned long long> g_tma_launches{0};   // launches of the bulk-tensor (TMA) 1D kernels
+const bool g_tail_enabled = [] { const char* e = getenv("SAVGOL_B200_NO_TAIL"); return !(e && e[0] == '1'); }();
+const bool g_phase_enabled = [] { const char* e = getenv("SAVGOL_B200_NO_PHASE"); return !(e && e[0] == '1'); }();
 std::atomic<int> g_tma_enabled{[] { const char* e = getenv("SAVGOL_B200_NO_TMA"); return (e && e[0] == '1') ? 0 : 1; }()};
 
 const Kernel1D* sg1d_group_table(int group)
@@ -89,6 +91,18 @@ bool encode_rows(EncodeTiled enc, CUtensorMap* m, const void* base, unsigned lon
 // fp32-pipe bound anyway (18 ... 32: -1 ... -9 %, except 26 where the cp.async instantiation is the slow one), and no
 // for launches of fewer than ~2048 segments, where the first tensor-map fetch is exposed latency (64 segments: 13 vs
 // 8 us).  g_tma_enabled: 0 off, 1 this rule, 2 always (tests).
+// Rows that end with 1..kTail outputs behind their last full segment (4097 = 4 x 1024 + 1): the generic kernel folds
+// them into that segment (Args1D::tail); counted for the worst per-row phase (misaligned rows start up to kPhase-1
+// outputs early).
+bool short_tail(const Args1D& a)
+{
+    if (!g_tail_enabled || a.len <= kTile) return false;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(a.in) | static_cast<uintptr_t>(a.in_row_bytes)) & 15) == 0;
+    const long long span = a.len + ((a.in_stride == 4 && !aligned && g_phase_enabled) ? kPhase - 1 : 0);
+    const long long over = span - (span - 1) / kTile * kTile;   // outputs in the last segment, 1..kTile
+    return over <= kTail;
+}
+
 bool tma_eligible(int n, int variant, const Args1D& a)
 {
     const int how = g_tma_enabled.load(std::memory_order_relaxed);
@@ -98,6 +112,7 @@ bool tma_eligible(int n, int variant, const Args1D& a)
     if (a.rows > 1 && ((a.in_row_bytes | a.out_row_bytes) & 15)) return false;
     if (a.rows >= (1LL << 31) || a.len >= (1LL << 36) || a.in_row_bytes >= (1LL << 40) || a.out_row_bytes >= (1LL << 40)) return false;
     if (how == 1) {
+        if (short_tail(a)) return false;   // 4 segments + tail beat 5 bulk-tensor segments
         if (!(n <= 17 || n == 26)) return false;
         if (((a.len + kTile - 1) / kTile) * a.rows < 2048) return false;
     }
@@ -187,6 +202,7 @@ cudaError_t sg1d_launch(int n, int variant, const W1D& w, Args1D& a, cudaStream_
         return cudaErrorInvalidValue;
     }
     a.out_tma = 0;
+    a.tail = a.phase = 0;
     if (a.pack_g == 0 && tma_eligible(n, variant, a)) {
         if (EncodeTiled enc = encode_tiled()) {
             const cudaError_t e = sg1d_launch_tma(enc, n, variant == V_STREAM_FAST ? VT_STREAM : VT_BATCH, w, a, stream);
@@ -226,8 +242,15 @@ cudaError_t sg1d_launch(int n, int variant, const W1D& w, Args1D& a, cudaStream_
         a.tiles_per_row = 1;
         a.ntiles = (a.rows + rpg - 1) / rpg;
     } else {
-        // work unit = segment of kTile (1024) outputs of one row, one warp each
-        a.tiles_per_row = (a.len + kTile - 1) / kTile;
+        // work unit = segment of kTile (1024) outputs of one row, one warp each.  Contiguous rows that are not
+        // 16-byte aligned start their segments up to kPhase-1 outputs early (per-row phase, sg1d_kernel.cuh)
+        const bool aligned = ((reinterpret_cast<uintptr_t>(a.in) | static_cast<uintptr_t>(a.in_row_bytes)) & 15) == 0;
+        a.phase = (a.in_stride == 4 && !aligned && g_phase_enabled) ? 1 : 0;
+        const long long span = a.len + (a.phase ? kPhase - 1 : 0);
+        a.tiles_per_row = (span + kTile - 1) / kTile;
+        // a last segment of <= kTail outputs would cost a whole pass of its warp: the segment before it takes them
+        a.tail = short_tail(a) ? 1 : 0;
+        if (a.tail) --a.tiles_per_row;
         a.ntiles = a.tiles_per_row * a.rows;
     }
     if (a.ntiles <= 0) return cudaSuccess;

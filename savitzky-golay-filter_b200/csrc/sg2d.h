@@ -14,6 +14,8 @@ enum : int { B_VALID = 0, B_CONSTANT = 1, B_REFLECT = 2 };
 struct Args2D {
     const float* in;
     float* out;
+    float* out1;            // multi-output launches (sg2d_multi.cu): images of the 2nd / 3rd component, same geometry,
+    float* out2;            // pitch and 16-byte phase as `out`
     const float* weights;   // device, [2ny+1][2nx+1]
     int rows, cols;         // input image size
     int out_rows, out_cols;
@@ -51,6 +53,10 @@ void plan_separable(int nx, int ny, int order, const double* coef, const float* 
 bool separable_supported(const Args2D& a, const SepPlan& plan);
 cudaError_t launch_separable(const Args2D& a, const SepPlan& plan, cudaStream_t stream);
 cudaError_t launch_additive(const Args2D& a, const SepPlan& plan, cudaStream_t stream);   // sg2d_add.cu
+// One launch for `n_out` (2 or 3) filters over the same images: the components of a gradient / Hessian (sg2d_multi.cu).
+// a.out / a.out1 / a.out2 receive the results; each plan carries its own scale in scales[i].
+bool multi_supported(const Args2D& a, const SepPlan* const* plans, int n_out);
+cudaError_t launch_multi(const Args2D& a, const SepPlan* const* plans, const float* scales, int n_out, cudaStream_t stream);
 // Ticket counter of one launch of the streaming kernels (sg2d_sep.cu): 4 zeroed bytes, stream ordered.
 cudaError_t acquire_counter(cudaStream_t stream, unsigned** out);
 

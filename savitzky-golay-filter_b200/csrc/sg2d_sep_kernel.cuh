@@ -98,6 +98,7 @@ struct SepW {
     float rk[R][16];        // rk[r][k-1]: weight of s_k = x[c+k] + sx * x[c-k], k = 1..n
     float col[R][33];       // column factor * scale, col[r][wy], wy = 0..2n
     float sx;               // +1 (even in x) / -1 (odd in x)
+    float sxo[3];           // multi-output kernels (gradient / Hessian): parity in x of every output's factors
 };
 
 // Tensor map of the input images for the bulk-tensor (TMA) staging of interior work items: {cols, rows, images},
@@ -225,11 +226,16 @@ __device__ __noinline__ void stage_rows4(unsigned d, const float* r0, const floa
         }
 }
 
-template <int N, int R, int RX, bool ADD>
-__global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? ((N <= 6 || (N == 7 && (R == 2 || R == 3))) ? SG2D_MINB : 3) : ((N >= 15 && R >= 3) ? SG2D_WIDE_MINB : SG2D_MINB2)) sep_kernel(const __grid_constant__ typename WSel<R, ADD>::type w,
+// NO > 1: the R factors form NO groups of R / NO, one group per OUTPUT image (the components of a gradient or a
+// Hessian, sg2d_multi.cu): every input row is staged and windowed once, each group has its own parity in x and its
+// own accumulator ring, and a completed row is stored to a.out, a.out1 (, a.out2).
+template <int N, int R, int RX, bool ADD, int NO = 1>
+__global__ void __launch_bounds__(kWarps * 32, NO > 1 ? ((N <= 2 && R <= 4 && NO == 2) ? 4 : 3) : ADD ? SG2D_ADD_MINB : RX >= 4 ? ((N <= 6 || (N == 7 && (R == 2 || R == 3))) ? SG2D_MINB : 3) : ((N >= 15 && R >= 3) ? SG2D_WIDE_MINB : SG2D_MINB2)) sep_kernel(const __grid_constant__ typename WSel<R, ADD>::type w,
                                                                             const __grid_constant__ Args2D a, const __grid_constant__ Tma2D maps)
 {
     static_assert(!ADD || (R == 1 && (RX == 4 || RX == 2) && N <= 16), "additive variant: one weight set, static ring");
+    static_assert(NO == 1 || (!ADD && R % NO == 0 && NO <= 3 && N <= 8), "multi-output variant: generic factors, static ring");
+    constexpr int RPO = R / NO;                 // factors per output
     constexpr int TW = 32 * RX;                 // output columns per strip
     constexpr int PADX = (N + 3) & ~3;          // staged row starts PADX columns left of the strip (16 B aligned)
     constexpr int DX = PADX - N;
@@ -239,7 +245,7 @@ __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? (
     // (n+1) copies of the column pass, which must stay inside the 32 KB instruction cache
     // (17x17 rank-4: 2448 FFMA2, measured 9 % slower than the shifting blocks)
     // (2 columns per lane, half-windows 9-16: the ring measured 9 % slower than the blocks at 25x25)
-    constexpr bool RING = ADD || (SG2D_RING && N <= 8 && (N + 1) * (2 * N + 1) * R * RX <= SG2D_RING_MAX);
+    constexpr bool RING = ADD || NO > 1 || (SG2D_RING && N <= 8 && (N + 1) * (2 * N + 1) * R * RX <= SG2D_RING_MAX);
     constexpr int NA = RING ? 2 * N + 2 : 2 * N + kU;   // output rows in flight per column
     constexpr int WIN = RX + DX + 2 * N;        // floats of the row window a lane touches
     constexpr int VW = RX >= 4 ? 4 : 2;         // floats per shared load
@@ -443,16 +449,18 @@ __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? (
 #pragma unroll 1
         for (int t = 0; t < kAhead; t += kStage) stage_rows(t);
 
-        // acc[jp][i]: partially accumulated output rows of the column pair (2jp, 2jp+1) of this lane.
+        // acc[0][jp][i]: partially accumulated output rows of the column pair (2jp, 2jp+1) of this lane.
         //   RING:  output row y (band-local, y = t - wy) lives in slot (y mod NA), NA = 2n+2; the main loop
         //          is unrolled over a full period of the ring (n+1 steps), so every index is static and
         //          no register ever moves.
         //   else:  slot i = output row (block base - 2n + i); blocks of kU rows end with a register shift.
-        float2 acc[RX / 2][NA];
+        float2 acc[NO][RX / 2][NA];
 #pragma unroll
-        for (int jp = 0; jp < RX / 2; ++jp)
+        for (int o = 0; o < NO; ++o)
 #pragma unroll
-            for (int i = 0; i < NA; ++i) acc[jp][i] = make_float2(0.f, 0.f);
+            for (int jp = 0; jp < RX / 2; ++jp)
+#pragma unroll
+                for (int i = 0; i < NA; ++i) acc[o][jp][i] = make_float2(0.f, 0.f);
 
         auto row_pass = [&](int t, float2 (&hp)[R][RX / 2]) {
           if constexpr (!ADD) {
@@ -480,11 +488,15 @@ __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? (
 #pragma unroll
                 for (int jp = 0; jp < RX / 2; ++jp) {
                     const int c0 = 2 * jp + DX + N;
-                    const float2 sk = make_float2(fmaf(w.sx, xs[c0 - k], xs[c0 + k]),      // +/-1 multiply is exact
-                                                  fmaf(w.sx, xs[c0 + 1 - k], xs[c0 + 1 + k]));
 #pragma unroll
-                    for (int r = 0; r < R; ++r)
-                        hp[r][jp] = __ffma2_rn(make_float2(w.rk[r][k - 1], w.rk[r][k - 1]), sk, hp[r][jp]);
+                    for (int o = 0; o < NO; ++o) {
+                        const float sxv = NO == 1 ? w.sx : w.sxo[o];
+                        const float2 sk = make_float2(fmaf(sxv, xs[c0 - k], xs[c0 + k]),      // +/-1 multiply is exact
+                                                      fmaf(sxv, xs[c0 + 1 - k], xs[c0 + 1 + k]));
+#pragma unroll
+                        for (int r = o * RPO; r < (o + 1) * RPO; ++r)
+                            hp[r][jp] = __ffma2_rn(make_float2(w.rk[r][k - 1], w.rk[r][k - 1]), sk, hp[r][jp]);
+                    }
                 }
           }
         };
@@ -543,21 +555,33 @@ __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? (
             for (int jp = 0; jp < RX / 2; ++jp) hB[jp] = make_float2(B[2 * jp], B[2 * jp + 1]);
           }
         };
-        auto emit = [&](const float2 (&v)[RX / 2]) {
+        auto emit_to = [&](float* drow, const float2 (&v)[RX / 2]) {
             if (st_vec) {
                 if constexpr (RX >= 4) {
 #pragma unroll
                     for (int q = 0; q < RX / 4; ++q)
-                        sg::st_cs_f4(dst_row + 4 * q, make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y));
+                        sg::st_cs_f4(drow + 4 * q, make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y));
                 } else {
-                    *reinterpret_cast<float2*>(dst_row) = v[0];
+                    *reinterpret_cast<float2*>(drow) = v[0];
                 }
             } else {
                 RowVals<RX> rv;
 #pragma unroll
                 for (int q = 0; q < RX / 2; ++q) rv.v[q] = v[q];
-                emit_ragged<RX>(dst_row, rv, X, Xlo, Xhi);
+                emit_ragged<RX>(drow, rv, X, Xlo, Xhi);
             }
+        };
+        auto emit = [&](const float2 (&v)[RX / 2]) {
+            emit_to(dst_row, v);
+            dst_row += a.out_stride;
+        };
+        // multi-output: the other images share geometry, pitch and 16-byte phase with a.out (the launcher checks),
+        // so they are a constant element offset away
+        const long long off1 = NO > 1 ? a.out1 - a.out : 0, off2 = NO > 2 ? a.out2 - a.out : 0;
+        auto emit_multi = [&](const float2 (&v)[NO][RX / 2]) {
+            emit_to(dst_row, v[0]);
+            if constexpr (NO > 1) emit_to(dst_row + off1, v[1]);
+            if constexpr (NO > 2) emit_to(dst_row + off2, v[2]);
             dst_row += a.out_stride;
         };
 
@@ -585,32 +609,32 @@ __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? (
                         // output row t - 2n: row t is its last window row (v = 0), row t+1 is outside
                         {
                             constexpr int i = (s2 - 2 * N + kOff) % NA;
-                            acc[jp][i] = __fadd2_rn(acc[jp][i], A0[jp]);
-                            v0[jp] = acc[jp][i];
+                            acc[0][jp][i] = __fadd2_rn(acc[0][jp][i], A0[jp]);
+                            v0[jp] = acc[0][jp][i];
                         }
                         // output row t + 1 - 2n: window rows 2n-1 (row t) and 2n (row t+1, v = 0)
                         {
                             constexpr int i = (s2 + 1 - 2 * N + kOff) % NA;
                             const float cw = w.col[2 * N - 1];
-                            acc[jp][i] = __ffma2_rn(make_float2(cw, cw), B0[jp], __fadd2_rn(acc[jp][i], P));
-                            v1[jp] = acc[jp][i];
+                            acc[0][jp][i] = __ffma2_rn(make_float2(cw, cw), B0[jp], __fadd2_rn(acc[0][jp][i], P));
+                            v1[jp] = acc[0][jp][i];
                         }
                         // output rows t - wy, wy = 1 .. 2n-2: window rows wy (row t) and wy + 1 (row t+1)
 #pragma unroll
                         for (int wy = 1; wy <= 2 * N - 2; ++wy) {
                             const int i = (s2 - wy + kOff) % NA;
                             const float c0w = w.col[wy], c1w = w.col[wy + 1];
-                            float2 r = __fadd2_rn(acc[jp][i], P);
+                            float2 r = __fadd2_rn(acc[0][jp][i], P);
                             r = __ffma2_rn(make_float2(c0w, c0w), B0[jp], r);
-                            acc[jp][i] = __ffma2_rn(make_float2(c1w, c1w), B1[jp], r);
+                            acc[0][jp][i] = __ffma2_rn(make_float2(c1w, c1w), B1[jp], r);
                         }
                         // output row t opens: window rows 0 (row t, v = 0) and 1 (row t+1)
                         {
                             const float cw = w.col[1];
-                            acc[jp][s2 % NA] = __ffma2_rn(make_float2(cw, cw), B1[jp], P);
+                            acc[0][jp][s2 % NA] = __ffma2_rn(make_float2(cw, cw), B1[jp], P);
                         }
                         // output row t + 1 opens with its window row 0 (v = 0)
-                        acc[jp][(s2 + 1) % NA] = A1[jp];
+                        acc[0][jp][(s2 + 1) % NA] = A1[jp];
                     }
                 });
                 phase = phase + 1 == NA / 2 ? 0 : phase + 1;
@@ -634,7 +658,7 @@ __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? (
                 row_pass(t, h0);
                 row_pass(t + 1, h1);
 
-                float2 v0[RX / 2], v1[RX / 2];
+                float2 v0[NO][RX / 2], v1[NO][RX / 2];
                 static_switch<NA / 2>(phase, [&](auto sc) {
                     constexpr int s2 = 2 * decltype(sc)::value;   // ring position of row t
                     // column pass: row t is window row wy of output row t - wy -> slot (s2 - wy) mod NA, row
@@ -647,28 +671,31 @@ __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? (
                             const float cw = w.col[r][wy];
                             constexpr int kOff = 4 * NA;   // keeps the modulo argument positive
                             const int i0 = (s2 - wy + kOff) % NA, i1 = (s2 + 1 - wy + kOff) % NA;
+                            const int o = r / RPO;
 #pragma unroll
                             for (int jp = 0; jp < RX / 2; ++jp) {
-                                if (wy == 0 && r == 0) {
-                                    acc[jp][i0] = __fmul2_rn(make_float2(cw, cw), h0[r][jp]);
-                                    acc[jp][i1] = __fmul2_rn(make_float2(cw, cw), h1[r][jp]);
+                                if (wy == 0 && r % RPO == 0) {
+                                    acc[o][jp][i0] = __fmul2_rn(make_float2(cw, cw), h0[r][jp]);
+                                    acc[o][jp][i1] = __fmul2_rn(make_float2(cw, cw), h1[r][jp]);
                                 } else {
-                                    acc[jp][i0] = __ffma2_rn(make_float2(cw, cw), h0[r][jp], acc[jp][i0]);
-                                    acc[jp][i1] = __ffma2_rn(make_float2(cw, cw), h1[r][jp], acc[jp][i1]);
+                                    acc[o][jp][i0] = __ffma2_rn(make_float2(cw, cw), h0[r][jp], acc[o][jp][i0]);
+                                    acc[o][jp][i1] = __ffma2_rn(make_float2(cw, cw), h1[r][jp], acc[o][jp][i1]);
                                 }
                             }
                         }
                     // output rows t - 2n and t + 1 - 2n are complete (their slots are dead until wy = 0 re-opens
                     // them, so these copies fold into the last FFMA2 of each row)
 #pragma unroll
-                    for (int jp = 0; jp < RX / 2; ++jp) {
-                        v0[jp] = acc[jp][(s2 + 2) % NA];
-                        v1[jp] = acc[jp][(s2 + 3) % NA];
-                    }
+                    for (int o = 0; o < NO; ++o)
+#pragma unroll
+                        for (int jp = 0; jp < RX / 2; ++jp) {
+                            v0[o][jp] = acc[o][jp][(s2 + 2) % NA];
+                            v1[o][jp] = acc[o][jp][(s2 + 3) % NA];
+                        }
                 });
                 phase = phase + 1 == NA / 2 ? 0 : phase + 1;
-                if (t >= 2 * N && t - 2 * N < nrows) emit(v0);
-                if (t + 1 >= 2 * N && t + 1 - 2 * N < nrows) emit(v1);
+                if (t >= 2 * N && t - 2 * N < nrows) emit_multi(v0);
+                if (t + 1 >= 2 * N && t + 1 - 2 * N < nrows) emit_multi(v1);
             }
         } else {
 #pragma unroll 1
@@ -693,8 +720,8 @@ __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? (
                                 const int i = u + 2 * N - wy;
 #pragma unroll
                                 for (int jp = 0; jp < RX / 2; ++jp) {
-                                    acc[jp][i] = __ffma2_rn(make_float2(cw, cw), h0[r][jp], acc[jp][i]);
-                                    acc[jp][i + 1] = __ffma2_rn(make_float2(cw, cw), h1[r][jp], acc[jp][i + 1]);
+                                    acc[0][jp][i] = __ffma2_rn(make_float2(cw, cw), h0[r][jp], acc[0][jp][i]);
+                                    acc[0][jp][i + 1] = __ffma2_rn(make_float2(cw, cw), h1[r][jp], acc[0][jp][i + 1]);
                                 }
                             }
 
@@ -702,13 +729,13 @@ __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? (
                         if (t >= 2 * N && t - 2 * N < nrows) {
                             float2 v[RX / 2];
 #pragma unroll
-                            for (int jp = 0; jp < RX / 2; ++jp) v[jp] = acc[jp][u];
+                            for (int jp = 0; jp < RX / 2; ++jp) v[jp] = acc[0][jp][u];
                             emit(v);
                         }
                         if (t + 1 >= 2 * N && t + 1 - 2 * N < nrows) {
                             float2 v[RX / 2];
 #pragma unroll
-                            for (int jp = 0; jp < RX / 2; ++jp) v[jp] = acc[jp][u + 1];
+                            for (int jp = 0; jp < RX / 2; ++jp) v[jp] = acc[0][jp][u + 1];
                             emit(v);
                         }
                     }
@@ -717,44 +744,19 @@ __global__ void __launch_bounds__(kWarps * 32, ADD ? SG2D_ADD_MINB : RX >= 4 ? (
 #pragma unroll
                 for (int jp = 0; jp < RX / 2; ++jp)
 #pragma unroll
-                    for (int i = 0; i < NA; ++i) acc[jp][i] = (i + kU < NA) ? acc[jp][i + kU] : make_float2(0.f, 0.f);
+                    for (int i = 0; i < NA; ++i) acc[0][jp][i] = (i + kU < NA) ? acc[0][jp][i + kU] : make_float2(0.f, 0.f);
             }
         }
         cp_async_wait<0>();
     }
 }
 
-template <int N, int R, bool ADD>
-cudaError_t launch_nr(const Args2D& a, const SepPlan& plan, cudaStream_t stream)
+// Grid, band height, ticket counter and launch of one instantiation `kern` (weights `w` already filled).
+// s_bps / s_sms: the instantiation's cached occupancy (function-local statics of the caller).
+template <int N, int RX, class K, class W>
+cudaError_t launch_common(K kern, const W& w, const Args2D& a, cudaStream_t stream, std::atomic<int>& s_bps, std::atomic<int>& s_sms)
 {
-    constexpr int RX = (N <= 8 && SG2D_RX4) ? SG2D_RXW : 2;
-    typename WSel<R, ADD>::type w;
-    const float sc = a.scale;
-    if constexpr (ADD) {
-        // W = u(x) + v(y): row[0] = u, col[0] = v with v(+-ny) = 0 (factor2d.cpp); both carry the scale
-        float u[2 * N + 1];
-        for (int k = 0; k <= 2 * N; ++k) u[k] = plan.row[0][k] * sc;
-        for (int j = 1; j <= 2 * N; ++j) w.pu[j] = make_float2(u[j], u[j - 1]);
-        w.pu[0] = make_float2(0.f, 0.f);
-        w.u_first = u[0];
-        w.u_last = u[2 * N];
-        for (int k = 0; k <= 2 * N; ++k) w.col[k] = plan.col[0][k] * sc;
-    } else {
-        for (int r = 0; r < R; ++r) {
-            // N = max(nx, ny): the shorter factor is centred and zero-padded (the extra taps multiply
-            // boundary-mapped, i.e. finite, samples by 0)
-            w.rc[r] = plan.row[r][plan.nx];
-            for (int k = 1; k <= N; ++k) w.rk[r][k - 1] = k <= plan.nx ? plan.row[r][plan.nx + k] : 0.0f;
-            for (int k = 0; k <= 2 * N; ++k) {
-                const int j = k - N + plan.ny;
-                w.col[r][k] = (j >= 0 && j <= 2 * plan.ny) ? plan.col[r][j] * sc : 0.0f;
-            }
-        }
-        w.sx = plan.parity_x < 0 ? -1.0f : 1.0f;
-    }
-    auto kern = sep_kernel<N, R, RX, ADD>;
     // resident CTAs per SM / SM count of this instantiation (same on every B200; filled once, any thread)
-    static std::atomic<int> s_bps{0}, s_sms{0};
     int bps = s_bps.load(std::memory_order_acquire), sms = s_sms.load(std::memory_order_acquire);
     if (bps == 0 || sms == 0) {
         int dev = 0, nb = 0;
@@ -818,6 +820,39 @@ cudaError_t launch_nr(const Args2D& a, const SepPlan& plan, cudaStream_t stream)
     ec = cudaGetLastError();
     const cudaError_t ef = cudaFreeAsync(aa.counter, stream);
     return ec != cudaSuccess ? ec : ef;
+}
+
+
+template <int N, int R, bool ADD>
+cudaError_t launch_nr(const Args2D& a, const SepPlan& plan, cudaStream_t stream)
+{
+    constexpr int RX = (N <= 8 && SG2D_RX4) ? SG2D_RXW : 2;
+    typename WSel<R, ADD>::type w;
+    const float sc = a.scale;
+    if constexpr (ADD) {
+        // W = u(x) + v(y): row[0] = u, col[0] = v with v(+-ny) = 0 (factor2d.cpp); both carry the scale
+        float u[2 * N + 1];
+        for (int k = 0; k <= 2 * N; ++k) u[k] = plan.row[0][k] * sc;
+        for (int j = 1; j <= 2 * N; ++j) w.pu[j] = make_float2(u[j], u[j - 1]);
+        w.pu[0] = make_float2(0.f, 0.f);
+        w.u_first = u[0];
+        w.u_last = u[2 * N];
+        for (int k = 0; k <= 2 * N; ++k) w.col[k] = plan.col[0][k] * sc;
+    } else {
+        for (int r = 0; r < R; ++r) {
+            // N = max(nx, ny): the shorter factor is centred and zero-padded (the extra taps multiply
+            // boundary-mapped, i.e. finite, samples by 0)
+            w.rc[r] = plan.row[r][plan.nx];
+            for (int k = 1; k <= N; ++k) w.rk[r][k - 1] = k <= plan.nx ? plan.row[r][plan.nx + k] : 0.0f;
+            for (int k = 0; k <= 2 * N; ++k) {
+                const int j = k - N + plan.ny;
+                w.col[r][k] = (j >= 0 && j <= 2 * plan.ny) ? plan.col[r][j] * sc : 0.0f;
+            }
+        }
+        w.sx = plan.parity_x < 0 ? -1.0f : 1.0f;
+    }
+    static std::atomic<int> s_bps{0}, s_sms{0};
+    return launch_common<N, RX>(sep_kernel<N, R, RX, ADD>, w, a, stream, s_bps, s_sms);
 }
 
 }  // namespace

@@ -11,6 +11,8 @@ constexpr int kThreads = 128;              // 4 warps per CTA
 constexpr int kR = 32;                     // consecutive outputs per thread (register sliding window)
 constexpr int kTile = 32 * kR;             // 1024 outputs per segment (one warp)
 constexpr int kSeg = kTile;
+constexpr int kPhase = 32;                  // generic kernel: misaligned rows start their segments on 128-byte lines, up to kPhase-1 outputs early
+constexpr int kTail = 32;                   // generic kernel: a row's last segment may carry up to kTail extra outputs, one per lane
 constexpr int kMaxN = 32;
 constexpr int kMaxWs = 2 * kMaxN + 1;      // 65, ref: include/iterative/savgolFilter.h:42
 
@@ -60,6 +62,8 @@ struct Args1D {
     int edge_lead, edge_trail;  // 1: outputs [0,n) / [len-n,len) come from the polynomial edge table
     long long tiles_per_row, ntiles;  // segments (1024 outputs) per row / in the launch; ntiles < 2^31
     int pack_g;              // short-row kernel (sg1d_packed.cuh): lanes per row (16, 8, 4); ntiles = row groups
+    int tail;                // generic kernel: 1 = the last segment of every row also produces the (<= kTail) outputs behind it
+    int phase;               // generic kernel: contiguous rows that are not 16-byte aligned are cut on a per-row phase (sg1d_kernel.cuh)
     int out_tma;             // TMA kernel (sg1d_tma.cuh): full segments are stored by one bulk-tensor copy
 };
 

@@ -268,3 +268,50 @@ def test_short_row_batches_share_warps(oracle, n, m, d, dt):
             assert np.max(np.abs(y - ref)) <= tol(xh, dt, d), (n, L, rows, mode, float(np.max(np.abs(y - ref))))
             assert torch.all(out[:, :off] == 7.0) and torch.all(out[:, off + L:] == 7.0), (n, L, rows)
             f.close()
+
+
+@pytest.mark.parametrize("n,m,d", [(16, 3, 1), (3, 2, 0), (32, 4, 2)])
+def test_misaligned_rows_and_short_tails(oracle, n, m, d):
+    """Rows that are not 16-byte aligned are cut on a per-row phase (segments start up to 3 outputs before the row),
+    and rows that end 1..32 outputs behind a full segment hand those to the segment before (sg1d_kernel.cuh).
+    Every phase of input and output, every boundary mode, lengths around the tail thresholds; both flavours."""
+    rng = np.random.default_rng(77 + n)
+    lengths = [1025, 1027, 1056, 1057, 2049, 2080, 2081, 3071, 4095, 4096, 4097, 4099, 4127, 4130]
+    for L in lengths:
+        rows = 5
+        for off_in, off_out, extra in [(0, 0, 0), (1, 1, 0), (2, 2, 1), (3, 3, 2), (1, 2, 3), (3, 0, 1), (0, 1, 0)]:
+            pitch = L + 3 + extra                          # odd pitches: the phase changes from row to row
+            mode = MODES[(L + off_in + extra) % 4]
+            big = rng.standard_normal((rows, pitch)).astype(np.float32)
+            x = big[:, off_in:off_in + L]
+            dbig = torch.from_numpy(big).cuda()
+            o = oracle.Filter1D(n, m, d, 1.0, mode)
+            f = sg.SavgolFilter(n, m, d, 1.0, mode)
+            ref = o.apply(np.ascontiguousarray(x))
+            out = torch.full((rows, pitch), 7.0, device="cuda")
+            f.apply(dbig[:, off_in:off_in + L], out=out[:, off_out:off_out + L])
+            got = out[:, off_out:off_out + L].cpu().numpy()
+            assert np.max(np.abs(got - ref)) <= parity_tol(x, 1.0), (L, off_in, off_out, pitch, mode)
+            assert torch.all(out[:, :off_out] == 7.0) and torch.all(out[:, off_out + L:] == 7.0), (L, off_in, off_out)
+            sg.set_exact(True)
+            out.fill_(7.0)
+            f.apply(dbig[:, off_in:off_in + L], out=out[:, off_out:off_out + L])
+            sg.set_exact(False)
+            assert np.array_equal(bits(out[:, off_out:off_out + L].cpu().numpy()), bits(ref)), (L, off_in, off_out, pitch, mode)
+            assert torch.all(out[:, :off_out] == 7.0) and torch.all(out[:, off_out + L:] == 7.0)
+            v = f.apply_valid(dbig[0, off_in:off_in + L])
+            sg.set_exact(True)
+            ve = f.apply_valid(dbig[0, off_in:off_in + L]).cpu().numpy()
+            sg.set_exact(False)
+            rv = o.apply_valid(np.ascontiguousarray(x[0]))
+            assert np.array_equal(bits(ve), bits(rv)) and np.max(np.abs(v.cpu().numpy() - rv)) <= parity_tol(x, 1.0)
+            f.close()
+    # the tail outputs use the operation order of the main loop: the interior of the fast result does not depend on
+    # where the row ends (4097 = four segments + a tail of 1; 5000 = five segments)
+    f = sg.SavgolFilter(n, m, d, 1.0, "reflect")
+    x = torch.from_numpy(rng.standard_normal(5000).astype(np.float32)).cuda()
+    long = f.apply(x).cpu().numpy()
+    for L in (4097, 4100, 4128):
+        for off in (0, 1, 2, 3):
+            short = f.apply(x[off:off + L]).cpu().numpy()
+            assert np.array_equal(bits(short[n:L - n]), bits(long[off + n:off + L - n])), (L, off)

@@ -236,3 +236,82 @@ def test_wrapper_components_run_concurrently_and_equal_the_single_filters():
     buf = torch.rand(300, 400, device="cuda")
     lib = sg.lib()
     assert lib.savgol2d_gradient(3, 3, 2, buf.data_ptr(), 300, 400, 400, buf.data_ptr(), buf.data_ptr(), 1.0, 1.0, 1) == 0
+
+
+def test_gradient_and_hessian_run_as_one_multi_output_launch():
+    """Half-windows <= 8: the components share ONE launch of the multi-output kernel (sg2d_multi.cu) -- the image is staged
+    once, each component has its own accumulator ring.  Same factors, same operation order per component as the
+    single filters: bit-identical results.  ref: src/savgol2d.c:462-558 (one savgol2d_apply per component)."""
+    lib = sg.lib()
+    g = torch.Generator(device="cuda").manual_seed(33)
+    for rows, cols in ((257, 1031), (1024, 1024), (64, 130)):
+        img = torch.rand(rows, cols, device="cuda", generator=g) - 0.5
+        for hw, order, b in ((1, 2, "constant"), (2, 2, "reflect"), (2, 3, "constant"), (3, 3, "reflect"), (3, 5, "constant"),
+                             (4, 4, "reflect"), (4, 5, "constant"), (2, 4, "reflect"), (5, 3, "reflect"), (7, 3, "constant"), (8, 5, "reflect")):
+            c0 = sg.launch_count()
+            gx, gy = sg.gradient(img, hw, hw, order, 0.5, 2.0, b)
+            c1 = sg.launch_count()
+            assert c1 - c0 == 1, (hw, order, c1 - c0)
+            comps = [(gx, 1, 0), (gy, 0, 1)]
+            if order >= 2:
+                hxx, hxy, hyy = sg.hessian(img, hw, hw, order, 0.5, 2.0, b)
+                assert sg.launch_count() - c1 == 1, (hw, order)
+                comps += [(hxx, 2, 0), (hxy, 1, 1), (hyy, 0, 2)]
+            for got, dx, dy in comps:
+                f = sg.Savgol2DFilter(hw, hw, order, dx, dy, 0.5, 2.0)
+                assert torch.equal(got, f.apply(img, b)), (rows, cols, hw, order, dx, dy, b)
+                f.close()
+    # rectangular windows and partial requests (only some components asked for)
+    img = torch.rand(300, 500, device="cuda", generator=g)
+    gx = torch.empty_like(img)
+    c0 = sg.launch_count()
+    assert lib.savgol2d_gradient(3, 2, 3, img.data_ptr(), 300, 500, 500, gx.data_ptr(), None, 1.0, 1.0, 2) == 0
+    assert sg.launch_count() - c0 == 1
+    f = sg.Savgol2DFilter(3, 2, 3, 1, 0)
+    assert torch.equal(gx, f.apply(img, "reflect"))
+    hxx, hyy = torch.empty_like(img), torch.empty_like(img)
+    c0 = sg.launch_count()
+    assert lib.savgol2d_hessian(3, 2, 3, img.data_ptr(), 300, 500, 500, hxx.data_ptr(), None, hyy.data_ptr(), 1.0, 1.0, 1) == 0
+    assert sg.launch_count() - c0 == 1
+    assert torch.equal(hxx, sg.Savgol2DFilter(3, 2, 3, 2, 0).apply(img, "constant"))
+    assert torch.equal(hyy, sg.Savgol2DFilter(3, 2, 3, 0, 2).apply(img, "constant"))
+    # outputs with different 16-byte phases keep the per-component launches, with the same numbers; aliased ones run in sequence
+    flat = torch.zeros(2 * 300 * 500 + 8, device="cuda")
+    o0, o1 = flat[:150000].view(300, 500), flat[150001:300001].view(300, 500)
+    c0 = sg.launch_count()
+    assert lib.savgol2d_gradient(2, 2, 2, img.data_ptr(), 300, 500, 500, o0.data_ptr(), o1.data_ptr(), 1.0, 1.0, 1) == 0
+    assert sg.launch_count() - c0 == 2
+    assert torch.equal(o0, sg.Savgol2DFilter(2, 2, 2, 1, 0).apply(img, "constant"))
+    assert torch.equal(o1, sg.Savgol2DFilter(2, 2, 2, 0, 1).apply(img, "constant"))
+    assert lib.savgol2d_gradient(2, 2, 2, img.data_ptr(), 300, 500, 500, o0.data_ptr(), o0.data_ptr(), 1.0, 1.0, 1) == 0
+    assert torch.equal(o0, sg.Savgol2DFilter(2, 2, 2, 0, 1).apply(img, "constant"))       # gy written last
+
+
+def test_host_image_wrappers_upload_once_and_match_the_device_path():
+    """Host images (the reference's calling convention): one upload, the device path, one download per component."""
+    lib = sg.lib()
+    rng = np.random.default_rng(12)
+    img = rng.random((300, 517)).astype(np.float32)
+    d = torch.from_numpy(img).cuda()
+    for hw, order, b in ((2, 2, "constant"), (3, 3, "reflect"), (9, 3, "constant")):
+        gx, gy = sg.gradient(img, hw, hw, order, 0.5, 2.0, b)
+        dgx, dgy = sg.gradient(d, hw, hw, order, 0.5, 2.0, b)
+        assert np.array_equal(bits(gx), bits(dgx.cpu().numpy())) and np.array_equal(bits(gy), bits(dgy.cpu().numpy())), (hw, order)
+        hs = sg.hessian(img, hw, hw, order, 0.5, 2.0, b)
+        ds = sg.hessian(d, hw, hw, order, 0.5, 2.0, b)
+        for a_, b_ in zip(hs, ds):
+            assert np.array_equal(bits(a_), bits(b_.cpu().numpy())), (hw, order)
+    # pitched host buffers; VALID leaves the border of the outputs untouched (ref: src/savgol2d.c:374-393)
+    big = rng.random((300, 600)).astype(np.float32)
+    gx = np.full((300, 600), 7.0, np.float32)
+    gy = np.full((300, 600), 7.0, np.float32)
+    assert lib.savgol2d_gradient(3, 2, 3, big.ctypes.data, 300, 517, 600, gx.ctypes.data, gy.ctypes.data, 1.0, 1.0, 0) == 0
+    fx, fy = sg.Savgol2DFilter(3, 2, 3, 1, 0), sg.Savgol2DFilter(3, 2, 3, 0, 1)
+    view = torch.from_numpy(np.ascontiguousarray(big[:, :517])).cuda()
+    wx, wy = fx.apply_valid(view).cpu().numpy(), fy.apply_valid(view).cpu().numpy()
+    assert np.array_equal(bits(gx[2:298, 3:514]), bits(wx)) and np.array_equal(bits(gy[2:298, 3:514]), bits(wy))
+    for g_ in (gx, gy):
+        assert np.all(g_[:2] == 7.0) and np.all(g_[298:] == 7.0) and np.all(g_[:, :3] == 7.0) and np.all(g_[:, 514:] == 7.0)
+    # overlapping host buffers keep the reference's component-by-component order
+    z = img.copy()
+    assert lib.savgol2d_gradient(2, 2, 2, z.ctypes.data, 300, 517, 517, z.ctypes.data, gy[:, :517].copy().ctypes.data, 1.0, 1.0, 1) == 0

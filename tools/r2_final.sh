@@ -18,4 +18,6 @@ for k,v in d['configs'].items(): show(k,v)
 "
 tail -3 gpurun_out/bench_all.err
 echo "== reference arm"; ( time timeout 600 python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err ) 2>&1 | tail -3; tail -c 300 gpurun_out/bench_ref.json
+timeout 300 python tools/perf_shapes.py > gpurun_out/r2_shapes_1d.txt 2>&1; sed -n 1,5p gpurun_out/r2_shapes_1d.txt
+timeout 600 python tools/r2_wrappers.py > gpurun_out/r2_wrappers.txt 2>&1; sed -n 1,4p gpurun_out/r2_wrappers.txt
 timeout 600 python tools/perf_shapes2d.py > gpurun_out/r2_shapes_2d.txt 2>&1; tail -2 gpurun_out/r2_shapes_2d.txt

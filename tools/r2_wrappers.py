@@ -1,5 +1,6 @@
-"""savgol2d_gradient / _hessian on device images: concurrent component launches (default) vs the sequential composition
-(SAVGOL_B200_WRAP_SEQ=1), and both against N x the single-filter time.  usage (GPU box): python tools/r2_wrappers.py"""
+"""savgol2d_gradient / _hessian on device images: ONE multi-output launch (default) vs concurrent per-component launches
+(SAVGOL_B200_WRAP_FUSED=0) vs the sequential composition (SAVGOL_B200_WRAP_SEQ=1), all against the single-filter time.
+usage (GPU box): python tools/r2_wrappers.py"""
 import os, subprocess, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
@@ -19,17 +20,23 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
             torch.cuda.synchronize()
             tot += e0.elapsed_time(e1)
         return tot / reps * 1e3
-    for size in (1024, 4096, 8192):
+    for hw, order in ((2, 2), (2, 3), (3, 3), (4, 4), (7, 3)):
+      for size in (1024, 4096, 8192):
         img = torch.rand(size, size, device="cuda")
-        f = sg.Savgol2DFilter(7, 7, 3, 1, 0)
+        f = sg.Savgol2DFilter(hw, hw, order, 1, 0)
         o1 = torch.empty_like(img)
         single = t(lambda: f.apply(img, "constant", out=o1))
-        g = t(lambda: sg.gradient(img, 7, 7, 3, 1.0, 1.0, "constant"))
-        h = t(lambda: sg.hessian(img, 7, 7, 3, 1.0, 1.0, "constant"))
-        lap = t(lambda: sg.laplacian(img, 7, 7, 3, 1.0, 1.0, "constant"))
-        print(f"{size}x{size}: single filter {single:7.1f} us | gradient {g:7.1f} us ({g / single:.2f}x) | hessian {h:7.1f} us ({h / single:.2f}x) | laplacian (one fused table) {lap:7.1f} us")
+        c0 = sg.launch_count()
+        sg.gradient(img, hw, hw, order, 1.0, 1.0, "constant")
+        nl = sg.launch_count() - c0
+        g = t(lambda: sg.gradient(img, hw, hw, order, 1.0, 1.0, "constant"))
+        h = t(lambda: sg.hessian(img, hw, hw, order, 1.0, 1.0, "constant"))
+        lap = t(lambda: sg.laplacian(img, hw, hw, order, 1.0, 1.0, "constant"))
+        print(f"{2 * hw + 1}x{2 * hw + 1} order {order} {size}x{size}: single filter {single:7.1f} us | gradient {g:7.1f} us ({g / single:.2f}x, {nl} launch) | hessian {h:7.1f} us ({h / single:.2f}x) | laplacian (one table) {lap:7.1f} us")
 else:
-    for seq in ("0", "1"):
-        print("== SAVGOL_B200_WRAP_SEQ=" + seq + (" (sequential composition)" if seq == "1" else " (concurrent component launches)"))
-        env = dict(os.environ, SAVGOL_B200_WRAP_SEQ=seq)
-        print(subprocess.run([sys.executable, __file__, "child"], capture_output=True, text=True, env=env).stdout)
+    for name, extra in (("default: ONE multi-output launch (half-windows <= 8)", {}),
+                        ("SAVGOL_B200_WRAP_FUSED=0: concurrent per-component launches", {"SAVGOL_B200_WRAP_FUSED": "0"}),
+                        ("SAVGOL_B200_WRAP_SEQ=1: sequential composition", {"SAVGOL_B200_WRAP_SEQ": "1"})):
+        print("== " + name, flush=True)
+        r = subprocess.run([sys.executable, __file__, "child"], capture_output=True, text=True, env=dict(os.environ, **extra))
+        print(r.stdout + r.stderr[-2000:], flush=True)

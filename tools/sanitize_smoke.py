@@ -97,6 +97,32 @@ so = [torch.empty(5000, device="cuda") for _ in range(3)]
 torch.cuda.synchronize()
 assert sg.lib().savgol_apply_slices(fh.handle, (C.c_void_p * 3)(*[t.data_ptr() for t in sl]), (C.c_void_p * 3)(*[t.data_ptr() for t in so]),
                                     (C.c_size_t * 3)(5000, 5000, 5000), devs, 3) == 0
+# misaligned rows on the per-row phase (every phase of input and output), short tails behind the last full segment
+for n, m, d, mode in [(3, 2, 0, "polynomial"), (16, 3, 1, "reflect"), (32, 4, 2, "periodic"), (10, 2, 1, "constant")]:
+    f = sg.SavgolFilter(n, m, d, 1.0, mode)
+    for L in (1025, 1056, 1057, 2049, 4095, 4097, 4130):
+        for off_in, off_out in ((0, 0), (1, 1), (2, 3), (3, 0), (5, 5), (31, 31)):
+            big = torch.from_numpy(rng.standard_normal((3, L + 40)).astype(np.float32)).cuda()
+            out = torch.empty(3, L + 40, device="cuda")
+            f.apply(big[:, off_in:off_in + L], out=out[:, off_out:off_out + L])
+        f.apply_valid(torch.from_numpy(rng.standard_normal(L + 1).astype(np.float32)).cuda()[1:])
+    f.close()
+sm = sg.SavgolMCStream(7, 10, 2, 1, 1.0)
+for K in (1030, 1056, 2049):
+    sm.push(torch.from_numpy(rng.standard_normal((7, K + 1)).astype(np.float32)).cuda()[:, 1:])
+# gradient / Hessian: one multi-output launch (every instantiated rank combination), host images uploaded once
+for hw, order in [(1, 2), (2, 2), (2, 3), (3, 5), (4, 4), (5, 3), (7, 3), (8, 5)]:
+    for shape in [(70, 260), (333, 131), (40, 1030)]:
+        img = torch.from_numpy(rng.random(shape).astype(np.float32)).cuda()
+        for b in ("constant", "reflect"):
+            sg.gradient(img, hw, hw, order, 1.0, 0.5, b)
+            sg.hessian(img, hw, hw, order, 1.0, 0.5, b)
+sg.gradient(rng.random((90, 200)).astype(np.float32), 3, 2, 3, 1.0, 1.0, "reflect")
+sg.hessian(rng.random((90, 200)).astype(np.float32), 2, 2, 2, 1.0, 1.0, "valid")
+# pageable host buffers larger than a bounce chunk (host copy pool + pinned bounce buffers)
+hb = rng.standard_normal((5000, 1100)).astype(np.float32)
+fh.apply(hb)
+fh.apply(hb, out=hb)
 sg.set_exact(True)
 f2 = sg.Savgol2DFilter(3, 2, 3)
 f2.apply(torch.from_numpy(rng.random((40, 50)).astype(np.float32)).cuda(), "reflect")
