@@ -96,9 +96,10 @@ bool encode_rows(EncodeTiled enc, CUtensorMap* m, const void* base, unsigned lon
 // outputs early).
 bool short_tail(const Args1D& a)
 {
-    if (!g_tail_enabled || a.len <= kTile) return false;
+    if (!g_tail_enabled) return false;
     const bool aligned = ((reinterpret_cast<uintptr_t>(a.in) | static_cast<uintptr_t>(a.in_row_bytes)) & 15) == 0;
     const long long span = a.len + ((a.in_stride == 4 && !aligned && g_phase_enabled) ? kPhase - 1 : 0);
+    if (span <= kTile) return false;   // one segment holds the row
     const long long over = span - (span - 1) / kTile * kTile;   // outputs in the last segment, 1..kTile
     return over <= kTail;
 }

@@ -23,6 +23,43 @@ __host__ __device__ constexpr int packed_slot_chunks(int n, int delta, int g)
     return phys;
 }
 
+// Where the sample that stands for x-index xi of ANY row comes from (sample_address of sg1d_kernel.cuh without the
+// row): kind 0 = sample idx of the row itself, 1 = entry idx of the row's left halo, 2 = of its right halo,
+// 3 = zero.  Rows of one launch share length, mode and halo layout, so the pad elements of a row slot are
+// described once per CTA (table in shared memory) instead of being re-derived for every row.
+constexpr int kPadKindShift = 28;
+template <int LEAD, int N>
+__device__ __forceinline__ int pad_source(const Args1D& a, int xi)
+{
+    const int len = static_cast<int>(a.len);
+    int idx = xi;
+    if (xi < 0) {
+        if (a.lhalo) {
+            const int h = LEAD + xi;
+            return h >= 0 ? ((1 << kPadKindShift) | h) : (3 << kPadKindShift);
+        }
+        switch (a.mode) {
+            case MODE_REFLECT: idx = -xi - 1; if (idx >= len) idx = len - 1; break;
+            case MODE_PERIODIC: idx = ((xi % len) + len) % len; break;
+            case MODE_CONSTANT: idx = 0; break;
+            default: return 3 << kPadKindShift;
+        }
+    } else if (xi >= len) {
+        if (a.rhalo) {
+            const int h = xi - len;
+            return h < N ? ((2 << kPadKindShift) | h) : (3 << kPadKindShift);
+        }
+        switch (a.mode) {
+            case MODE_REFLECT: idx = 2 * len - xi - 1; if (idx < 0) idx = 0; break;
+            case MODE_PERIODIC: idx = xi % len; break;
+            case MODE_CONSTANT: idx = len - 1; break;
+            default: return 3 << kPadKindShift;
+        }
+    }
+    return idx;
+}
+constexpr int kPadTabMax = 128;   // pad elements of a row slot: PAD (<= 64) on the left, <= n + 9 on the right
+
 template <int N, bool LEAD2N>
 __global__ void __launch_bounds__(kThreads, N <= 18 ? 4 : 3) sg1d_packed_kernel(const __grid_constant__ W1D W, const __grid_constant__ Args1D a)
 {
@@ -54,6 +91,15 @@ __global__ void __launch_bounds__(kThreads, N <= 18 ? 4 : 3) sg1d_packed_kernel(
     const unsigned stride = gridDim.x * kWarps;
     const bool out_aligned = a.out_stride == 4 && ((reinterpret_cast<uintptr_t>(a.out) | static_cast<uintptr_t>(a.out_row_bytes)) & 15) == 0;
 
+    // pad table of a row slot: element el of the slot buffer (float position el + 4 * (el >> 5)) <- pad_source(el - PAD)
+    __shared__ int2 s_pad[kPadTabMax];
+    const int nl = 4 * c_lo, nrest = nl + 4 * (nch - c_hi);
+    for (int q = threadIdx.x; q < nrest; q += kThreads) {
+        const int el = q < nl ? q : 4 * c_hi + (q - nl);
+        s_pad[q] = make_int2(pad_source<LEAD, N>(a, el - PAD), el + 4 * (el >> 5));
+    }
+    __syncthreads();   // the only CTA-wide barrier: once, before the warps go their own ways
+
     // stage this lane's share of row `row` into slot `slot` of `buf`
     auto stage = [&](float4* buf, long long row) {
         if (row >= a.rows) return;
@@ -69,13 +115,15 @@ __global__ void __launch_bounds__(kThreads, N <= 18 ? 4 : 3) sg1d_packed_kernel(
                 cp_async4(reinterpret_cast<float*>(sbuf + c + (c >> 3)) + (e & 3), src0 + static_cast<long long>(e) * a.in_stride);
             }
         }
-        const int nl = 4 * c_lo, nrest = nl + 4 * (nch - c_hi);
+        // pad elements: source and destination come from the CTA's table
+        float* sf = reinterpret_cast<float*>(sbuf);
         for (int q = p; q < nrest; q += g) {
-            const int el = q < nl ? q : 4 * c_hi + (q - nl);
-            const int c = el >> 2;
-            float* d = reinterpret_cast<float*>(sbuf + c + (c >> 3)) + (el & 3);
-            const float* sp = sample_address<LEAD, N>(a, xrow, row, static_cast<long long>(el) - PAD);
-            if (sp) cp_async4(d, sp);
+            const int2 e = s_pad[q];
+            const int kind = e.x >> kPadKindShift, idx = e.x & ((1 << kPadKindShift) - 1);
+            float* d = sf + e.y;
+            if (kind == 0) cp_async4(d, xrow + static_cast<long long>(idx) * a.in_stride);
+            else if (kind == 1) cp_async4(d, a.lhalo + row * a.lhalo_pitch + idx);
+            else if (kind == 2) cp_async4(d, a.rhalo + row * a.rhalo_pitch + idx);
             else *d = 0.0f;
         }
     };
