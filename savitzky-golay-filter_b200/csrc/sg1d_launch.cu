@@ -124,7 +124,7 @@ int g_sms[64];
 std::mutex g_mu;
 }  // namespace
 
-constexpr size_t kPackedSmemMax = 110 * 1024;  // two CTAs per SM
+constexpr size_t kPackedSmemMax = 106 * 1024;  // two CTAs per SM next to the kernel's 4 KB of static tables
 
 // dynamic shared memory of the short-row kernel: 2 buffers per warp of 32/g row slots + edge values
 static size_t packed_smem_bytes(int n, bool lead2n, int g)
@@ -190,20 +190,26 @@ cudaError_t sg1d_launch(int n, int variant, const W1D& w, Args1D& a, cudaStream_
     int gi_idx = 0;
     size_t smem = 0;
     a.pack_g = 0;
-    if ((variant == V_BATCH_FAST || variant == V_STREAM_FAST) && a.len <= 512 && a.rows > 1) {
+    a.tail = a.phase = 0;
+    // contiguous rows that are not all 16-byte aligned: row slots / segments start on a per-row phase (up to 3 outputs
+    // early in the short-row kernel, up to kPhase-1 in the generic one) so that their chunks are aligned in memory
+    const bool in_aligned = ((reinterpret_cast<uintptr_t>(a.in) | static_cast<uintptr_t>(a.in_row_bytes)) & 15) == 0;
+    const bool phase = a.in_stride == 4 && !in_aligned && g_phase_enabled;
+    const long long plen = a.len + (phase ? 3 : 0);   // outputs a short row's slot must hold
+    if ((variant == V_BATCH_FAST || variant == V_STREAM_FAST) && plen <= 512 && a.rows > 1) {
         // lanes per row; wide windows on very short rows would need more shared memory per row slot than
         // two resident CTAs allow: fewer, wider slots then
-        int g = a.len <= 32 ? 1 : a.len <= 64 ? 2 : a.len <= 128 ? 4 : a.len <= 256 ? 8 : 16;
+        int g = plen <= 32 ? 1 : plen <= 64 ? 2 : plen <= 128 ? 4 : plen <= 256 ? 8 : 16;
+        a.phase = phase ? 1 : 0;
         while (g < 16 && packed_smem_bytes(n, variant == V_STREAM_FAST, g) > kPackedSmemMax) g *= 2;
         a.pack_g = g;
         gi_idx = g == 1 ? 0 : g == 2 ? 1 : g == 4 ? 2 : g == 8 ? 3 : 4;
         smem = packed_smem_bytes(n, variant == V_STREAM_FAST, g);
-        variant = variant == V_BATCH_FAST ? V_PACK_BATCH_FAST : V_PACK_STREAM_FAST;
+        variant = variant == V_BATCH_FAST ? (phase ? V_PACK_BATCH_FAST_PH : V_PACK_BATCH_FAST) : (phase ? V_PACK_STREAM_FAST_PH : V_PACK_STREAM_FAST);
     } else if (variant >= V_PACK_BATCH_FAST) {
         return cudaErrorInvalidValue;
     }
     a.out_tma = 0;
-    a.tail = a.phase = 0;
     if (a.pack_g == 0 && tma_eligible(n, variant, a)) {
         if (EncodeTiled enc = encode_tiled()) {
             const cudaError_t e = sg1d_launch_tma(enc, n, variant == V_STREAM_FAST ? VT_STREAM : VT_BATCH, w, a, stream);
@@ -219,7 +225,7 @@ cudaError_t sg1d_launch(int n, int variant, const W1D& w, Args1D& a, cudaStream_
     {
         std::lock_guard<std::mutex> lk(g_mu);
         GridInfo& gi = g_grid[n][variant][gi_idx];
-        if (smem > 48 * 1024) {   // per device and function; cheap enough to repeat
+        if (smem + 6 * 1024 > 48 * 1024) {   // (the limit counts the kernel's ~5 KB of static tables too) per device and function; cheap enough to repeat
             e = cudaFuncSetAttribute(k.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kPackedSmemMax));
             if (e != cudaSuccess) return e;
         }

@@ -60,7 +60,8 @@ __device__ __forceinline__ int pad_source(const Args1D& a, int xi)
 }
 constexpr int kPadTabMax = 128;   // pad elements of a row slot: PAD (<= 64) on the left, <= n + 9 on the right
 
-template <int N, bool LEAD2N>
+// PHASE: rows that are not 16-byte aligned start their slot on a per-row phase (the launcher picks the instantiation).
+template <int N, bool LEAD2N, bool PHASE>
 __global__ void __launch_bounds__(kThreads, N <= 18 ? 4 : 3) sg1d_packed_kernel(const __grid_constant__ W1D W, const __grid_constant__ Args1D a)
 {
     constexpr int LEAD = LEAD2N ? 2 * N : N;
@@ -83,29 +84,48 @@ __global__ void __launch_bounds__(kThreads, N <= 18 ? 4 : 3) sg1d_packed_kernel(
 
     const long long len = a.len;
     const int ilen = static_cast<int>(len);
-    const int nch = (ilen + 2 * N + DELTA + 3) >> 2;          // chunks of a row the compute loop may touch
-    const int c_lo = PAD / 4;                                  // o0 == 0: first chunk made of four existing samples
-    const int c_all = (ilen + PAD) >> 2;
-    const int c_hi = c_all < nch ? c_all : nch;
     const unsigned ngroups = static_cast<unsigned>(a.ntiles);
     const unsigned stride = gridDim.x * kWarps;
     const bool out_aligned = a.out_stride == 4 && ((reinterpret_cast<uintptr_t>(a.out) | static_cast<uintptr_t>(a.out_row_bytes)) & 15) == 0;
 
-    // pad table of a row slot: element el of the slot buffer (float position el + 4 * (el >> 5)) <- pad_source(el - PAD)
-    __shared__ int2 s_pad[kPadTabMax];
-    const int nl = 4 * c_lo, nrest = nl + 4 * (nch - c_hi);
-    for (int q = threadIdx.x; q < nrest; q += kThreads) {
-        const int el = q < nl ? q : 4 * c_hi + (q - nl);
-        s_pad[q] = make_int2(pad_source<LEAD, N>(a, el - PAD), el + 4 * (el >> 5));
+    // Geometry of a row slot.  Slot position 0 <-> x index -sh - PAD, where sh is the row's PHASE: 0 for rows whose
+    // first sample is 16-byte aligned (and for every row of a launch without PHASE), else (address of x[0] / 4)
+    // mod 4 -- the slot of a misaligned contiguous row starts up to 3 outputs early so that its 16-byte chunks are
+    // aligned in global memory (same idea as the per-row phase of sg1d_kernel.cuh; outputs before 0 are never
+    // stored).  Per phase: chunks [c_lo, c_hi) consist of four existing samples and are copied whole; the other
+    // nrest elements -- pads, ragged ends -- are described ONCE per CTA by a table:
+    // element el of the slot (float position el + 4 * (el >> 5)) <- pad_source(el - PAD - sh).
+    __shared__ int2 s_pad[4][kPadTabMax];
+    __shared__ int s_geo[4][4];   // c_lo, c_hi, nrest, (unused)
+    const int nphase = PHASE ? 4 : 1;
+    for (int sh = 0; sh < nphase; ++sh) {
+        const int nch = (ilen + sh + 2 * N + DELTA + 3) >> 2;      // chunks of a row the compute loop may touch
+        const int c_lo = (PAD + sh + 3) >> 2;                      // first chunk made of four existing samples
+        const int c_all = (ilen + sh + PAD) >> 2;
+        const int c_hi = c_all < nch ? c_all : nch;
+        const int nl = 4 * c_lo, nrest = nl + 4 * (nch - c_hi);
+        if (threadIdx.x == 0) { s_geo[sh][0] = c_lo; s_geo[sh][1] = c_hi; s_geo[sh][2] = nrest; s_geo[sh][3] = 0; }
+        for (int q = threadIdx.x; q < nrest; q += kThreads) {
+            const int el = q < nl ? q : 4 * c_hi + (q - nl);
+            s_pad[sh][q] = make_int2(pad_source<LEAD, N>(a, el - PAD - sh), el + 4 * (el >> 5));
+        }
     }
     __syncthreads();   // the only CTA-wide barrier: once, before the warps go their own ways
+    // launches without phases keep their (single) geometry in registers
+    const int c_lo0 = (PAD + 3) >> 2;
+    const int nch0 = (ilen + 2 * N + DELTA + 3) >> 2, c_all0 = (ilen + PAD) >> 2;
+    const int c_hi0 = c_all0 < nch0 ? c_all0 : nch0;
+    const int nrest0 = 4 * c_lo0 + 4 * (nch0 - c_hi0);
+    auto row_phase = [&](const char* xrow) -> int { return PHASE ? static_cast<int>((reinterpret_cast<uintptr_t>(xrow) >> 2) & 3) : 0; };
 
     // stage this lane's share of row `row` into slot `slot` of `buf`
     auto stage = [&](float4* buf, long long row) {
         if (row >= a.rows) return;
         const char* xrow = a.in + row * a.in_row_bytes;
         float4* sbuf = buf + slot * SLOT;
-        const char* src0 = xrow - static_cast<long long>(PAD) * a.in_stride;
+        const int sh = row_phase(xrow);
+        const int c_lo = PHASE ? s_geo[sh][0] : c_lo0, c_hi = PHASE ? s_geo[sh][1] : c_hi0, nrest = PHASE ? s_geo[sh][2] : nrest0;
+        const char* src0 = xrow - static_cast<long long>(PAD + sh) * a.in_stride;
         const bool vec_ok = (a.in_stride == 4) && ((reinterpret_cast<uintptr_t>(src0) & 15) == 0);
         if (vec_ok) {
             for (int c = c_lo + p; c < c_hi; c += g) cp_async16(sbuf + c + (c >> 3), src0 + 16LL * c);
@@ -118,7 +138,7 @@ __global__ void __launch_bounds__(kThreads, N <= 18 ? 4 : 3) sg1d_packed_kernel(
         // pad elements: source and destination come from the CTA's table
         float* sf = reinterpret_cast<float*>(sbuf);
         for (int q = p; q < nrest; q += g) {
-            const int2 e = s_pad[q];
+            const int2 e = s_pad[sh][q];
             const int kind = e.x >> kPadKindShift, idx = e.x & ((1 << kPadKindShift) - 1);
             float* d = sf + e.y;
             if (kind == 0) cp_async4(d, xrow + static_cast<long long>(idx) * a.in_stride);
@@ -164,12 +184,13 @@ __global__ void __launch_bounds__(kThreads, N <= 18 ? 4 : 3) sg1d_packed_kernel(
         float out[kR];
         compute_fast<N, DELTA>(sb, W, out);
 
-        const int o = kR * p;  // first output of this lane inside its row
+        const int sh = active ? row_phase(xrow) : 0;
+        const int o = kR * p - sh;  // first output of this lane inside its row
         if (a.edge_lead || a.edge_trail) {
 #pragma unroll
             for (int j = 0; j < kR; ++j) {
                 const int oj = o + j;
-                if (a.edge_lead && oj < N) out[j] = se[oj];
+                if (a.edge_lead && oj < N) { if (oj >= 0) out[j] = se[oj]; }
                 else if (a.edge_trail && oj >= ilen - N && oj < ilen) out[j] = se[N + (ilen - 1 - oj)];
             }
         }
@@ -177,7 +198,7 @@ __global__ void __launch_bounds__(kThreads, N <= 18 ? 4 : 3) sg1d_packed_kernel(
         // stream: hand the last state_w samples of [lead pad | x] to the next chunk (always staged here)
         if (a.state_out != nullptr && active) {
             const float* bf = reinterpret_cast<const float*>(buf_cur + slot * SLOT);
-            const int first = ilen - a.state_w + PAD;    // buffer position of the oldest carried sample
+            const int first = ilen - a.state_w + PAD + sh;    // buffer position of the oldest carried sample
             for (int i = p; i < a.state_w; i += g) {
                 float v;
                 if (first >= 0) { const int pos = first + i; v = bf[4 * ((pos >> 2) + (pos >> 5)) + (pos & 3)]; }
@@ -198,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, N <= 18 ? 4 : 3) sg1d_packed_kernel(
             const int lim = static_cast<int>(a.out_len < len ? a.out_len : len);
             const long long row0 = static_cast<long long>(grp) * rpg;
             const int shift = 36 - __clz(g);                  // log2(outputs parked per slot) = 5 + log2(g)
-            if (out_aligned) {
+            if (out_aligned && !PHASE) {
                 // chunk q = lane + 32 i of the group's parked outputs: 512 contiguous bytes per store
 #pragma unroll
                 for (int i = 0; i < kR / 4; ++i) {
@@ -216,15 +237,42 @@ __global__ void __launch_bounds__(kThreads, N <= 18 ? 4 : 3) sg1d_packed_kernel(
                         }
                     }
                 }
+            } else if (a.out_stride == 4) {
+                // chunk q = lane + 32 i of the group's parked outputs (contiguous rows: 512 contiguous bytes per store).
+                // Chunk c of a row holds outputs 4c - sh .. 4c - sh + 3; it is one 16-byte store when it lies inside
+                // the row and its address is aligned (always, when the output row has the phase of the input row)
+#pragma unroll
+                for (int i = 0; i < kR / 4; ++i) {
+                    const int q = lane + 32 * i;
+                    const int s_ = q >> (shift - 2), c = q & (8 * g - 1);
+                    const long long r_ = row0 + s_;
+                    if (r_ < a.rows) {
+                        const int o4 = 4 * c - row_phase(a.in + r_ * a.in_row_bytes);   // first output of the chunk
+                        if (o4 < lim && o4 + 4 > 0) {
+                            const float4 v = buf_cur[s_ * SLOT + c + (c >> 3)];
+                            float* dst = reinterpret_cast<float*>(a.out + r_ * a.out_row_bytes) + o4;
+                            if (o4 >= 0 && o4 + 4 <= lim && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) st_cs_f4(dst, v);
+                            else {
+                                if (o4 >= 0) dst[0] = v.x;
+                                if (o4 + 1 >= 0 && o4 + 1 < lim) dst[1] = v.y;
+                                if (o4 + 2 >= 0 && o4 + 2 < lim) dst[2] = v.z;
+                                if (o4 + 3 >= 0 && o4 + 3 < lim) dst[3] = v.w;
+                            }
+                        }
+                    }
+                }
             } else {
 #pragma unroll 4
                 for (int i = 0; i < kR; ++i) {
                     const int q = lane + 32 * i;             // flat index over the group's parked outputs
                     const int s_ = q >> shift, f = q & ((1 << shift) - 1);
                     const long long r_ = row0 + s_;
-                    if (f < lim && r_ < a.rows) {
-                        const float v = reinterpret_cast<const float*>(buf_cur + s_ * SLOT)[f + 4 * (f >> 5)];
-                        *reinterpret_cast<float*>(a.out + r_ * a.out_row_bytes + static_cast<long long>(f) * a.out_stride) = v;
+                    if (r_ < a.rows) {
+                        const int of = f - row_phase(a.in + r_ * a.in_row_bytes);   // parked position f holds output f - sh
+                        if (of >= 0 && of < lim) {
+                            const float v = reinterpret_cast<const float*>(buf_cur + s_ * SLOT)[f + 4 * (f >> 5)];
+                            *reinterpret_cast<float*>(a.out + r_ * a.out_row_bytes + static_cast<long long>(of) * a.out_stride) = v;
+                        }
                     }
                 }
             }

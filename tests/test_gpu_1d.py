@@ -315,3 +315,46 @@ def test_misaligned_rows_and_short_tails(oracle, n, m, d):
         for off in (0, 1, 2, 3):
             short = f.apply(x[off:off + L]).cpu().numpy()
             assert np.array_equal(bits(short[n:L - n]), bits(long[off + n:off + L - n])), (L, off)
+
+
+@pytest.mark.parametrize("n,m,d", [(2, 2, 0), (10, 2, 1), (16, 3, 1), (32, 5, 0)])
+def test_short_misaligned_rows_in_the_packed_kernel(oracle, n, m, d):
+    """Short rows (several per warp, sg1d_packed.cuh) that are not 16-byte aligned: their slot starts on the row's
+    phase (up to 3 outputs early) so that the 16-byte copies and stores stay aligned; the pad elements of a slot come
+    from a per-CTA table.  Lengths around every packing class, every phase of input and output, every mode."""
+    rng = np.random.default_rng(500 + n)
+    ws = 2 * n + 1
+    for L in sorted({ws, ws + 1, 29, 30, 33, 48, 61, 62, 63, 64, 65, 100, 125, 126, 127, 128, 129, 250, 253, 254, 255, 256, 360, 509, 510, 511, 512}):
+        if L < ws:
+            continue
+        rows = 37
+        for off_in, off_out, extra in [(0, 0, 0), (1, 1, 0), (2, 2, 1), (3, 3, 2), (1, 3, 1), (0, 2, 3)]:
+            pitch = L + 3 + extra
+            mode = MODES[(L + off_in + extra) % 4]
+            big = rng.standard_normal((rows, pitch)).astype(np.float32)
+            x = big[:, off_in:off_in + L]
+            dbig = torch.from_numpy(big).cuda()
+            o = oracle.Filter1D(n, m, d, 1.0, mode)
+            f = sg.SavgolFilter(n, m, d, 1.0, mode)
+            ref = o.apply(np.ascontiguousarray(x))
+            out = torch.full((rows, pitch), 7.0, device="cuda")
+            f.apply(dbig[:, off_in:off_in + L], out=out[:, off_out:off_out + L])
+            got = out[:, off_out:off_out + L].cpu().numpy()
+            assert np.max(np.abs(got - ref)) <= parity_tol(x, 1.0), (L, off_in, off_out, pitch, mode)
+            assert torch.all(out[:, :off_out] == 7.0) and torch.all(out[:, off_out + L:] == 7.0), (L, off_in, off_out)
+            f.close()
+    # the multichannel stream with short misaligned chunks (carried state = left halo of the slot)
+    C_, K = 41, 77
+    sig = rng.standard_normal((C_, 6 * K + 3)).astype(np.float32)
+    dsig = torch.from_numpy(sig).cuda()
+    o = oracle.Filter1D(n, m, d, 1.0)
+    want = np.stack([o.stream_run(r[1:1 + 6 * K]) for r in sig])
+    st = sg.SavgolMCStream(C_, n, m, d, 1.0)
+    parts = []
+    for k in range(6):
+        out, cnt = st.push(dsig[:, 1 + k * K:1 + (k + 1) * K])
+        parts.append(out[:, :cnt].cpu().numpy())
+    out, cnt = st.flush(dsig)
+    parts.append(out[:, :cnt].cpu().numpy())
+    got = np.concatenate(parts, axis=1)
+    assert got.shape == want.shape and np.max(np.abs(got - want)) <= parity_tol(sig, 1.0)
