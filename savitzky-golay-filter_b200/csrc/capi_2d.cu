@@ -157,6 +157,42 @@ int apply2d_any(const Savgol2DFilter* f, const float* in, int rows, int cols, in
     }
     const size_t img_in = static_cast<size_t>(rows) * cols, img_out = static_cast<size_t>(orows) * ocols;
     P.begin(in, out);
+    // A few LARGE images (the reference's call: ONE image) give an image-per-slot pipeline nothing to overlap: upload,
+    // kernel and download would run one after the other.  They are cut into row bands with ny halo rows instead --
+    // the band entry point of the multi-GPU path, bit-identical to the whole-image result -- and the bands travel
+    // through the slots.  Measured on B200 (tools/r2_host_small.py, profiles/r2_host_small.txt): one pinned 4096 x 4096
+    // image 2.47 -> 1.94 ms, pageable 4.35 -> 3.29 ms; three images already overlap image by image.
+    static const bool no_bands = [] { const char* e = getenv("SAVGOL_B200_NO_HOST_BANDS"); return e && e[0] == '1'; }();
+    const size_t band_floats = std::min<size_t>(sge::chunk_floats(P.bounce_in || P.bounce_out), size_t(8) << 18);   // ~8 MiB bands
+    if (!no_bands && boundary != sg2d::B_VALID && sge::exact_mode() == 0 && n_images < 3 && img_in >= 2 * band_floats &&
+        aside.empty() && !ranges_overlap2d(in, (n_images - 1) * ipitch + static_cast<size_t>(rows - 1) * is + cols, out,
+                                           (n_images - 1) * opitch + static_cast<size_t>(rows - 1) * os + cols)) {
+        int rows_b = static_cast<int>(std::max<size_t>(band_floats / cols, 1));
+        rows_b = std::max(rows_b & ~1, std::max(2 * ny, 16));            // even: the additive kernel pairs even image rows
+        const int nb = std::max(1, rows / rows_b);                       // the last band takes the remainder (< 2 rows_b rows)
+        if (nb >= 2) {
+            const size_t cap_rows = static_cast<size_t>(2 * rows_b + 2 * ny);
+            if (!P.ensure(cap_rows * cols, static_cast<size_t>(2 * rows_b) * cols)) return -1;
+            size_t u = 0;
+            for (size_t i = 0; i < n_images; ++i)
+                for (int b = 0; b < nb; ++b, ++u) {
+                    const int s = static_cast<int>(u % sge::Pipeline::kSlots);
+                    const int r0 = b * rows_b, r1 = b + 1 == nb ? rows : r0 + rows_b;
+                    const int top = r0 > 0 ? ny : 0, bot = r1 < rows ? ny : 0, nbuf = r1 - r0 + top + bot;
+                    if (!P.reuse(s)) return -1;
+                    if (!P.h2d(s, P.d_in[s], cols, in + i * ipitch + static_cast<size_t>(r0 - top) * is, is, cols, nbuf)) return -1;
+                    cudaEventRecord(P.e_in[s], P.s_in);
+                    cudaStreamWaitEvent(P.s_k, P.e_in[s], 0);
+                    if (u >= sge::Pipeline::kSlots) cudaStreamWaitEvent(P.s_k, P.e_out[s], 0);
+                    if (!run2d_device(f, P.d_in[s], nbuf, cols, cols, 0, P.d_out[s], cols, 0, 1, boundary, P.s_k, top, bot, r0 - top)) return -1;   // image row of the buffer's first row
+                    cudaEventRecord(P.e_k[s], P.s_k);
+                    cudaStreamWaitEvent(P.s_out, P.e_k[s], 0);
+                    if (!P.d2h(s, out + i * opitch + static_cast<size_t>(r0) * os, os, P.d_out[s], cols, cols, r1 - r0)) return -1;
+                    cudaEventRecord(P.e_out[s], P.s_out);
+                }
+            return P.finish() ? 0 : -1;
+        }
+    }
     if (!P.ensure(img_in, img_out)) return -1;
     for (size_t i = 0; i < n_images; ++i) {
         const int s = static_cast<int>(i % sge::Pipeline::kSlots);

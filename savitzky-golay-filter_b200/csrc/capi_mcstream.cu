@@ -232,7 +232,7 @@ long long savgol_mcstream_push(SavgolMCStream* s, const float* input, size_t in_
     sge::Pipeline& P = *lease;
     const size_t K = chunk_len;
     const size_t opitch = (K + static_cast<size_t>(s->ws) + 3) & ~static_cast<size_t>(3);   // 16-byte aligned rows
-    const size_t cb = std::max<size_t>(1, std::min(s->channels, P.begin(input, output) / opitch));
+    const size_t cb = std::max<size_t>(1, std::min(s->channels, P.begin(input, output, s->channels * opitch) / opitch));
     if (!P.ensure(cb * K, cb * opitch)) return -1;
     cudaEvent_t prior = nullptr;
     if (cudaEventCreateWithFlags(&prior, cudaEventDisableTiming) == cudaSuccess) {

@@ -84,8 +84,10 @@ struct Pipeline {
     Pending pend[kSlots] = {};                    // D2H landed (or landing) in h_out[slot], still to be handed to the caller
     unsigned long long seq = 0;
 
-    // Start of a host-pointer call: classifies its buffers.  Returns the staging chunk in floats.
-    size_t begin(const void* in, const void* out);
+    // Start of a host-pointer call: classifies its buffers.  Returns the staging chunk in floats: the configured
+    // chunk (64 MiB; 16 MiB through bounce buffers), shrunk for calls of `total` floats that would otherwise fit one or
+    // two chunks and leave H2D, kernel and D2H nothing to overlap with (about eight chunks, never below 2 MiB).
+    size_t begin(const void* in, const void* out, size_t total = 0);
     // Streams / events on first use, slots (and bounce buffers, when this call needs them) grown on demand.
     // The current device must be `dev`.
     bool ensure(size_t need_in, size_t need_out);

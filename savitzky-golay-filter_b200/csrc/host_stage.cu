@@ -159,13 +159,24 @@ void host_copy2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
 int copy_threads() { return CopyPool::get().threads(); }
 
 // ---------------------------------------------------------------------------------------------
-size_t Pipeline::begin(const void* in, const void* out)
+size_t Pipeline::begin(const void* in, const void* out, size_t total)
 {
     static const bool off = [] { const char* e = getenv("SAVGOL_B200_NO_BOUNCE"); return e && atoi(e) != 0; }();
     bounce_in = !off && in && classify(in) == MemKind::Pageable;
     bounce_out = !off && out && classify(out) == MemKind::Pageable;
     for (Pending& p : pend) p.dst = nullptr;
-    return chunk_floats(bounce_in || bounce_out);
+    size_t chunk = chunk_floats(bounce_in || bounce_out);
+    static const bool fixed = [] { const char* e = getenv("SAVGOL_B200_FIXED_CHUNK"); return e && e[0] == '1'; }();
+    if (total >= (size_t(8) << 18) && !fixed) {
+        // measured on B200 (pinned, tools/r2_host_small.py): 64 MiB each way as one chunk 2.44 ms (H2D, kernel and D2H in
+        // sequence), as eight chunks 1.68 ms; 16 MiB: 0.65 -> 0.54 ms.  Below ~8 MiB the per-chunk launch and event
+        // latencies outweigh the overlap (4 MB: 0.25 ms as one chunk, 0.37 ms as two).
+        const size_t floor_ = std::min<size_t>(chunk, size_t(2) << 18);   // 2 MiB: below that the link efficiency drops
+        // (through bounce buffers every chunk also costs a wake-up of the host copy pool: four chunks, not eight --
+        // 64 MiB pageable: 2.8 ms in 16 MiB chunks, 3.4 ms in 8 MiB chunks)
+        chunk = std::min(chunk, std::max(floor_, total / ((bounce_in || bounce_out) ? 4 : 8)));
+    }
+    return chunk;
 }
 
 bool Pipeline::reuse(int s)
@@ -379,7 +390,7 @@ bool run1d_host_range(Pipeline& P, const SavgolFilter* f, const float* x, size_t
     const size_t n = f->config.half_window;
     const size_t ws = 2 * n + 1;
     const size_t padl = (n + 3) & ~static_cast<size_t>(3);
-    const size_t piece = P.begin(x, y);
+    const size_t piece = P.begin(x, y, b > a ? b - a : 0);
     if (b <= a) return true;
     if ((a != 0 && a < n) || (b != L && b + n > L) || b > L) {   // a cut must leave n real samples on its far side (or be a true end)
         fprintf(stderr, "savgol_b200: internal: host range [%lu, %lu) of %lu samples is closer than half_window to an end\n",
@@ -463,7 +474,7 @@ bool run1d_host(const SavgolFilter* f, const float* in, float* out, size_t rows,
     PipeLease lease;
     if (!lease.ok()) return false;
     Pipeline& P = *lease;
-    const size_t chunk = P.begin(in, out);
+    const size_t chunk = P.begin(in, out, rows * len);
 
     if (len > chunk) {
         for (size_t r = 0; r < rows; ++r)

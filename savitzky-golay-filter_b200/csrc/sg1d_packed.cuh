@@ -58,7 +58,7 @@ __device__ __forceinline__ int pad_source(const Args1D& a, int xi)
     }
     return idx;
 }
-constexpr int kPadTabMax = 128;   // pad elements of a row slot: PAD (<= 64) on the left, <= n + 9 on the right
+constexpr int kPadTabMax = 112;   // pad elements of a row slot: <= PAD + 4 (<= 68) on the left, <= n + 9 on the right
 
 // PHASE: rows that are not 16-byte aligned start their slot on a per-row phase (the launcher picks the instantiation).
 template <int N, bool LEAD2N, bool PHASE>
@@ -95,8 +95,8 @@ __global__ void __launch_bounds__(kThreads, N <= 18 ? 4 : 3) sg1d_packed_kernel(
     // stored).  Per phase: chunks [c_lo, c_hi) consist of four existing samples and are copied whole; the other
     // nrest elements -- pads, ragged ends -- are described ONCE per CTA by a table:
     // element el of the slot (float position el + 4 * (el >> 5)) <- pad_source(el - PAD - sh).
-    __shared__ int2 s_pad[4][kPadTabMax];
-    __shared__ int s_geo[4][4];   // c_lo, c_hi, nrest, (unused)
+    __shared__ int2 s_pad[PHASE ? 4 : 1][kPadTabMax];   // (static shared memory counts against the resident CTAs: keep it small)
+    __shared__ int s_geo[PHASE ? 4 : 1][4];   // c_lo, c_hi, nrest, (unused)
     const int nphase = PHASE ? 4 : 1;
     for (int sh = 0; sh < nphase; ++sh) {
         const int nch = (ilen + sh + 2 * N + DELTA + 3) >> 2;      // chunks of a row the compute loop may touch
