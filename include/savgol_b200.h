@@ -194,8 +194,13 @@ int savgol2d_apply(const Savgol2DFilter *filter,
                    const float *input, int rows, int cols, int in_stride,
                    float *output, int out_stride, Savgol2DBoundary boundary);
 
-/* ref: savgol2d.h:195-241 / src/savgol2d.c:462-618.  Host-pointer or device-pointer
- * images; each requested component is one filter create + apply, as in the reference. */
+/* ref: savgol2d.h:195-241 / src/savgol2d.c:462-618.  Host-pointer or device-pointer images.  Every requested
+ * component equals savgol2d_apply with that component's filter (the reference's composition) bit for bit, but the
+ * image is read once: device images with half-windows <= 8 run all components in ONE multi-output launch
+ * (others: concurrent per-component launches), host images are uploaded once.  Buffers that overlap each other fall
+ * back to the reference's component-by-component order.  The filters of recent configurations are cached.
+ * The Laplacian runs as one filter whose table is Wxx/dx^2 + Wyy/dy^2 (exact flavour: the reference's two filters
+ * and an add). */
 int savgol2d_gradient(int half_win_x, int half_win_y, int poly_order,
                       const float *input, int rows, int cols, int stride,
                       float *grad_x, float *grad_y,
