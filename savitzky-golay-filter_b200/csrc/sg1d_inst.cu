@@ -1,5 +1,5 @@
 // sg1d_inst.cu -- explicit instantiations of sg1d_kernel for four half-windows.
-// Compiled eight times (-DSG_GROUP=0..7) so the 288 fully unrolled kernels build in parallel.
+// Compiled eight times (-DSG_GROUP=0..7) so the 352 fully unrolled kernels build in parallel.
 #include "sg1d_kernel.cuh"
 #include "sg1d_packed.cuh"
 #include "sg1d_launch.h"
@@ -15,7 +15,8 @@ namespace sg {
     {&sg1d_kernel<N, false, ARITH_FAST>}, {&sg1d_kernel<N, false, ARITH_EXACT4>},                   \
     {&sg1d_kernel<N, false, ARITH_EXACTSEQ>}, {&sg1d_kernel<N, true, ARITH_FAST>},                  \
     {&sg1d_kernel<N, true, ARITH_EXACTSEQ>}, {&sg1d_packed_kernel<N, false, false>}, {&sg1d_packed_kernel<N, true, false>}, \
-    {&sg1d_packed_kernel<N, false, true>}, {&sg1d_packed_kernel<N, true, true>}
+    {&sg1d_packed_kernel<N, false, true>}, {&sg1d_packed_kernel<N, true, true>},                \
+    {&sg1d_kernel<N, false, ARITH_FAST, true>}, {&sg1d_kernel<N, true, ARITH_FAST, true>}
 
 #define SG_CAT_(a, b) a##b
 #define SG_CAT(a, b) SG_CAT_(a, b)

@@ -329,20 +329,23 @@ __device__ __forceinline__ void compute_exact(const float4* __restrict__ sb, con
 // warps per SM about 80 KB of loads are in flight per SM at any time.
 
 
-template <int N, int DELTA>
+template <int N, int DELTA, bool PT>
 struct Smem1D {
-    static constexpr int kSegChunks = (kSeg + kTail + 2 * N + DELTA + 3) / 4;
+    static constexpr int kSegChunks = (kSeg + (PT ? kTail : 0) + 2 * N + DELTA + 3) / 4;
     static constexpr int kSegPhys = kSegChunks + (kSegChunks >> 3) + 1;
 };
 
-template <int N, bool LEAD2N, int ARITH>
+// PT: the instantiation that knows about per-row phases and short tails (misaligned rows, rows ending just behind a
+// full segment; FAST flavours only).  Aligned launches keep the lean PT = false kernel: the extra paths cost the
+// compute-bound wide windows 5 % (config 3: 1.148 -> 1.21 ms) through instruction-cache pressure alone.
+template <int N, bool LEAD2N, int ARITH, bool PT = false>
 __global__ void __launch_bounds__(kThreads, SG_MIN_BLOCKS) sg1d_kernel(const __grid_constant__ W1D W, const __grid_constant__ Args1D a)
 {
     constexpr int LEAD = LEAD2N ? 2 * N : N;
     constexpr int DELTA = Geo<LEAD>::DELTA;
     constexpr int WS = 2 * N + 1;
     constexpr int kWarps = kThreads / 32;
-    using SM = Smem1D<N, DELTA>;
+    using SM = Smem1D<N, DELTA, PT>;
 
     __shared__ float4 s_buf[kWarps][2][SM::kSegPhys];
     __shared__ float s_edge[kWarps][2 * kMaxN];
@@ -375,12 +378,12 @@ __global__ void __launch_bounds__(kThreads, SG_MIN_BLOCKS) sg1d_kernel(const __g
     // The first segment then begins before output 0; those outputs are computed from whatever is staged and never
     // stored.  a.phase is set by the launcher, which also counts the segments per row for the worst phase.
     const char* xrow = a.in + row * a.in_row_bytes;
-    auto row_phase = [&](const char* r) -> long long { return a.phase ? static_cast<long long>((reinterpret_cast<uintptr_t>(r) >> 2) & (kPhase - 1)) : 0; };
+    auto row_phase = [&](const char* r) -> long long { return (PT && a.phase) ? static_cast<long long>((reinterpret_cast<uintptr_t>(r) >> 2) & (kPhase - 1)) : 0; };
     long long o0 = static_cast<long long>(t) * kSeg - row_phase(xrow);
     // a.tail: rows end with up to kTail outputs behind their last segment (launcher: a nearly empty extra segment
     // would cost a full pass of the warp); that segment stages the extra samples and each lane adds one output.
-    const int tail_cap = a.tail ? kSeg + kTail : kSeg;
-    if (seg < nseg && o0 < len) {
+    const int tail_cap = (PT && a.tail) ? kSeg + kTail : kSeg;
+    if (seg < nseg && (!PT || o0 < len)) {
         const long long l64 = len - o0;
         stage_segment<LEAD, N>(buf_cur + lane_chunk, buf_cur, a, xrow, row, o0, static_cast<int>(l64 < kBig ? l64 : kBig),
                                t + 1 == spr ? tail_cap : kSeg, rows_aligned, lane);
@@ -396,14 +399,14 @@ __global__ void __launch_bounds__(kThreads, SG_MIN_BLOCKS) sg1d_kernel(const __g
         const long long no0 = static_cast<long long>(nt) * kSeg - row_phase(nxrow);
         if (seg + stride < nseg) {
             const long long l64 = len - no0;
-            if (l64 > 0)   // (a phase-shifted row may not reach into its last segment)
+            if (!PT || l64 > 0)   // (a phase-shifted row may not reach into its last segment)
                 stage_segment<LEAD, N>(buf_nxt + lane_chunk, buf_nxt, a, nxrow, nrow, no0,
                                        static_cast<int>(l64 < kBig ? l64 : kBig), nt + 1 == spr ? tail_cap : kSeg, rows_aligned, lane);
         }
         cp_async_commit();
-        const bool has_tail = a.tail && t + 1 == spr;
+        const bool has_tail = PT && a.tail && t + 1 == spr;
         const int seg_cap = has_tail ? kSeg + kTail : kSeg;
-        if (o0 < len) {
+        if (!PT || o0 < len) {
 
         // polynomial edge outputs that fall into this segment (global reads, independent of the
         // staged data): one lane per output.  ref: src/savgolFilter.c:769-784
@@ -479,7 +482,7 @@ __global__ void __launch_bounds__(kThreads, SG_MIN_BLOCKS) sg1d_kernel(const __g
             float* dst = reinterpret_cast<float*>(orow) + o0 + 4 * lane;
             const float4* src = buf_cur + lane + (lane >> 3);
             // (phase-shifted first segment: outputs before 0 do not exist; they lie in the first chunks only, kPhase <= 128)
-            const int lo = o0 < 0 ? static_cast<int>(-o0) - 4 * lane : 0;   // (o0 exceeds 32 bits on long signals)
+            const int lo = (PT && o0 < 0) ? static_cast<int>(-o0) - 4 * lane : 0;   // (o0 exceeds 32 bits on long signals)
             if (lo <= 0) {
                 st_cs_f4(dst, src[0]);
             } else if (lo < 4) {
@@ -492,8 +495,8 @@ __global__ void __launch_bounds__(kThreads, SG_MIN_BLOCKS) sg1d_kernel(const __g
             for (int i = 1; i < kR / 4; ++i) st_cs_f4(dst + 128 * i, src[36 * i]);  // chunk lane + 32 i
         } else {
             const int lim = remain < kSeg ? static_cast<int>(remain) : kSeg;
-            const int lo = o0 < 0 ? static_cast<int>(-o0) : 0;
-            if (out_vec) store_cut(buf_cur + lane + (lane >> 3), reinterpret_cast<float*>(orow) + o0 + 4 * lane, lo - 4 * lane, lim - 4 * lane);
+            const int lo = (PT && o0 < 0) ? static_cast<int>(-o0) : 0;
+            if (PT && out_vec) store_cut(buf_cur + lane + (lane >> 3), reinterpret_cast<float*>(orow) + o0 + 4 * lane, lo - 4 * lane, lim - 4 * lane);
             else store_scalar(reinterpret_cast<const float*>(buf_cur) + lane, orow + (o0 + lane) * a.out_stride, a.out_stride, lo - lane, lim - lane);
         }
         if (has_tail) {

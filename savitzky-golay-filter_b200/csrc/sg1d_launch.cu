@@ -119,7 +119,7 @@ bool tma_eligible(int n, int variant, const Args1D& a)
     }
     return true;
 }
-GridInfo g_grid[kMaxN + 1][V_COUNT][5];  // per (n, variant, packing); filled lazily (same value on every B200)
+GridInfo g_grid[kMaxN + 1][V_COUNT][10];  // per (n, variant, packing x edge values); filled lazily (same value on every B200)
 int g_sms[64];
 std::mutex g_mu;
 }  // namespace
@@ -127,12 +127,14 @@ std::mutex g_mu;
 constexpr size_t kPackedSmemMax = 106 * 1024;  // two CTAs per SM next to the kernel's 4 KB of static tables
 
 // dynamic shared memory of the short-row kernel: 2 buffers per warp of 32/g row slots + edge values
-static size_t packed_smem_bytes(int n, bool lead2n, int g)
+static size_t packed_smem_bytes(int n, bool lead2n, int g, bool edges)
 {
     const int lead = lead2n ? 2 * n : n;
     const int delta = ((lead + 3) & ~3) - lead;
     const int rpg = 32 / g, warps = kThreads / 32;
-    return static_cast<size_t>(warps) * 2 * rpg * packed_slot_chunks(n, delta, g) * 16 + static_cast<size_t>(warps) * rpg * 2 * n * 4;
+    // the polynomial edge values (2n per row slot) live behind the buffers; launches without polynomial edges do not
+    // pay for them (64-sample rows, n = 16: 70 KB instead of 78 KB per CTA -> three resident CTAs instead of two)
+    return static_cast<size_t>(warps) * 2 * rpg * packed_slot_chunks(n, delta, g) * 16 + (edges ? static_cast<size_t>(warps) * rpg * 2 * n * 4 : 0);
 }
 
 static cudaError_t sg1d_launch_tma(EncodeTiled enc, int n, int vt, const W1D& w, Args1D& a, cudaStream_t stream)
@@ -201,10 +203,11 @@ cudaError_t sg1d_launch(int n, int variant, const W1D& w, Args1D& a, cudaStream_
         // two resident CTAs allow: fewer, wider slots then
         int g = plen <= 32 ? 1 : plen <= 64 ? 2 : plen <= 128 ? 4 : plen <= 256 ? 8 : 16;
         a.phase = phase ? 1 : 0;
-        while (g < 16 && packed_smem_bytes(n, variant == V_STREAM_FAST, g) > kPackedSmemMax) g *= 2;
+        const bool edges = a.edge_lead || a.edge_trail;
+        while (g < 16 && packed_smem_bytes(n, variant == V_STREAM_FAST, g, edges) > kPackedSmemMax) g *= 2;
         a.pack_g = g;
-        gi_idx = g == 1 ? 0 : g == 2 ? 1 : g == 4 ? 2 : g == 8 ? 3 : 4;
-        smem = packed_smem_bytes(n, variant == V_STREAM_FAST, g);
+        gi_idx = (g == 1 ? 0 : g == 2 ? 1 : g == 4 ? 2 : g == 8 ? 3 : 4) + (edges ? 5 : 0);
+        smem = packed_smem_bytes(n, variant == V_STREAM_FAST, g, edges);
         variant = variant == V_BATCH_FAST ? (phase ? V_PACK_BATCH_FAST_PH : V_PACK_BATCH_FAST) : (phase ? V_PACK_STREAM_FAST_PH : V_PACK_STREAM_FAST);
     } else if (variant >= V_PACK_BATCH_FAST) {
         return cudaErrorInvalidValue;
@@ -215,6 +218,19 @@ cudaError_t sg1d_launch(int n, int variant, const W1D& w, Args1D& a, cudaStream_
             const cudaError_t e = sg1d_launch_tma(enc, n, variant == V_STREAM_FAST ? VT_STREAM : VT_BATCH, w, a, stream);
             if (e != cudaErrorNotSupported) return e;   // NotSupported: the driver refused a tensor map -> generic kernel
         }
+    }
+    // generic kernel: misaligned rows / short tails take the PT instantiation of the FAST flavours (the exact flavours
+    // stage misaligned rows with 4-byte copies, as before)
+    if (a.pack_g == 0 && (variant == V_BATCH_FAST || variant == V_STREAM_FAST)) {
+        const long long span = a.len + (phase ? kPhase - 1 : 0);
+        a.phase = phase ? 1 : 0;
+        a.tiles_per_row = (span + kTile - 1) / kTile;
+        // a last segment of <= kTail outputs would cost a whole pass of its warp: the segment before it takes them
+        a.tail = short_tail(a) ? 1 : 0;
+        if (a.tail) --a.tiles_per_row;
+        if (a.phase || a.tail) variant = variant == V_BATCH_FAST ? V_BATCH_FAST_PT : V_STREAM_FAST_PT;
+    } else if (a.pack_g == 0) {
+        a.tiles_per_row = (a.len + kTile - 1) / kTile;
     }
     const Kernel1D& k = sg1d_group_table((n - 1) / 4)[((n - 1) % 4) * V_COUNT + variant];
 
@@ -249,15 +265,7 @@ cudaError_t sg1d_launch(int n, int variant, const W1D& w, Args1D& a, cudaStream_
         a.tiles_per_row = 1;
         a.ntiles = (a.rows + rpg - 1) / rpg;
     } else {
-        // work unit = segment of kTile (1024) outputs of one row, one warp each.  Contiguous rows that are not
-        // 16-byte aligned start their segments up to kPhase-1 outputs early (per-row phase, sg1d_kernel.cuh)
-        const bool aligned = ((reinterpret_cast<uintptr_t>(a.in) | static_cast<uintptr_t>(a.in_row_bytes)) & 15) == 0;
-        a.phase = (a.in_stride == 4 && !aligned && g_phase_enabled) ? 1 : 0;
-        const long long span = a.len + (a.phase ? kPhase - 1 : 0);
-        a.tiles_per_row = (span + kTile - 1) / kTile;
-        // a last segment of <= kTail outputs would cost a whole pass of its warp: the segment before it takes them
-        a.tail = short_tail(a) ? 1 : 0;
-        if (a.tail) --a.tiles_per_row;
+        // work unit = segment of kTile (1024) outputs of one row, one warp each (tiles_per_row: see above)
         a.ntiles = a.tiles_per_row * a.rows;
     }
     if (a.ntiles <= 0) return cudaSuccess;

@@ -10,7 +10,8 @@ namespace sg {
 enum : int { V_BATCH_FAST = 0, V_BATCH_EXACT4 = 1, V_BATCH_EXACTSEQ = 2, V_STREAM_FAST = 3, V_STREAM_EXACTSEQ = 4,
               V_PACK_BATCH_FAST = 5, V_PACK_STREAM_FAST = 6,  // short rows, several per warp (sg1d_packed.cuh)
               V_PACK_BATCH_FAST_PH = 7, V_PACK_STREAM_FAST_PH = 8,  // ... misaligned rows on a per-row phase
-              V_COUNT = 9 };
+              V_BATCH_FAST_PT = 9, V_STREAM_FAST_PT = 10,  // generic kernel with per-row phases / short tails (sg1d_kernel.cuh, PT)
+              V_COUNT = 11 };
 
 struct Kernel1D {
     void (*kernel)(const W1D, const Args1D);  // __global__ entry
