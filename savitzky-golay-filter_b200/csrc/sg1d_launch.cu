@@ -94,10 +94,16 @@ bool encode_rows(EncodeTiled enc, CUtensorMap* m, const void* base, unsigned lon
 // Rows that end with 1..kTail outputs behind their last full segment (4097 = 4 x 1024 + 1): the generic kernel folds
 // them into that segment (Args1D::tail); counted for the worst per-row phase (misaligned rows start up to kPhase-1
 // outputs early).
+// every row of the launch starts on a 16-byte boundary (the pitch of a single row does not matter)
+bool rows_aligned16(const Args1D& a)
+{
+    return ((reinterpret_cast<uintptr_t>(a.in) | (a.rows > 1 ? static_cast<uintptr_t>(a.in_row_bytes) : 0)) & 15) == 0;
+}
+
 bool short_tail(const Args1D& a)
 {
     if (!g_tail_enabled) return false;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(a.in) | static_cast<uintptr_t>(a.in_row_bytes)) & 15) == 0;
+    const bool aligned = rows_aligned16(a);
     const long long span = a.len + ((a.in_stride == 4 && !aligned && g_phase_enabled) ? kPhase - 1 : 0);
     if (span <= kTile) return false;   // one segment holds the row
     const long long over = span - (span - 1) / kTile * kTile;   // outputs in the last segment, 1..kTile
@@ -195,7 +201,7 @@ cudaError_t sg1d_launch(int n, int variant, const W1D& w, Args1D& a, cudaStream_
     a.tail = a.phase = 0;
     // contiguous rows that are not all 16-byte aligned: row slots / segments start on a per-row phase (up to 3 outputs
     // early in the short-row kernel, up to kPhase-1 in the generic one) so that their chunks are aligned in memory
-    const bool in_aligned = ((reinterpret_cast<uintptr_t>(a.in) | static_cast<uintptr_t>(a.in_row_bytes)) & 15) == 0;
+    const bool in_aligned = rows_aligned16(a);
     const bool phase = a.in_stride == 4 && !in_aligned && g_phase_enabled;
     const long long plen = a.len + (phase ? 3 : 0);   // outputs a short row's slot must hold
     if ((variant == V_BATCH_FAST || variant == V_STREAM_FAST) && plen <= 512 && a.rows > 1) {

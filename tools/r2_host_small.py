@@ -46,7 +46,15 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
             dev = f2.apply(torch.from_numpy(img).cuda(), "reflect").cpu().numpy()
             assert np.array_equal(o, op.numpy()) and np.array_equal(o, dev)
             print(f"[{tag:12s}] 2D {2 * hw + 1}x{2 * hw + 1} image(s) {str(shape):18s}: pinned {tp:8.3f} ms ({img.size / tp / 1e6:6.2f} Gpixel/s) | pageable {tg:8.3f} ms ({img.size / tg / 1e6:6.2f})", flush=True)
+    # gradient / Hessian of ONE host image: one upload + one multi-output launch + a download per component
+    # (SAVGOL_B200_WRAP_SEQ=1: the reference's composition, every component uploads the image again)
+    img = rng.random((4096, 4096), dtype=np.float32)
+    ip = pin(img)
+    for name, fn in (("gradient 5x5", lambda im: sg.gradient(im, 2, 2, 2, 1.0, 1.0, "constant")), ("hessian 5x5", lambda im: sg.hessian(im, 2, 2, 2, 1.0, 1.0, "constant"))):
+        tp = timeit(lambda: fn(ip), reps=5)
+        tg = timeit(lambda: fn(img), reps=5)
+        print(f"[{tag:12s}] 2D {name} of one host 4096x4096 image (outputs allocated per call): pinned input {tp:8.3f} ms | pageable {tg:8.3f} ms", flush=True)
     sys.exit(0)
 
-for tag, env in (("adaptive", {}), ("one chunk", {"SAVGOL_B200_NO_HOST_BANDS": "1", "SAVGOL_B200_FIXED_CHUNK": "1"})):
+for tag, env in (("adaptive", {}), ("one chunk", {"SAVGOL_B200_NO_HOST_BANDS": "1", "SAVGOL_B200_FIXED_CHUNK": "1", "SAVGOL_B200_WRAP_SEQ": "1"})):
     subprocess.run([sys.executable, os.path.abspath(__file__), "child", tag], env=dict(os.environ, **env), check=False)
