@@ -472,20 +472,54 @@ int run_components(int hx, int hy, int order, const float* in, int rows, int col
         if (plain && sge::device_ready(true)) {
             cudaStream_t st = sge::current_stream();
             const size_t img = static_cast<size_t>(rows) * cols;
+            // the copies travel in row bands through a leased staging pipeline: pinned memory by DMA, pageable memory
+            // through the pinned bounce buffers and the host copy pool (host_stage.cu)
+            sge::PipeLease lease;
+            if (!lease.ok()) return -1;
+            sge::Pipeline& P = *lease;
+            const float* some_out = comps[0].out;
+            for (int i = 1; i < n; ++i)
+                if (sge::classify(comps[i].out) == MemKind::Pageable) some_out = comps[i].out;
+            P.begin(in, some_out);
+            const int rows_b = static_cast<int>(std::max<size_t>(1, std::min<size_t>(rows, (size_t(8) << 18) / cols)));   // ~8 MiB
+            if (!P.ensure(static_cast<size_t>(rows_b) * cols, static_cast<size_t>(rows_b) * cols)) return -1;
             float* d = nullptr;
             if (!cuda_ok(cudaMallocAsync(&d, (n + 1) * img * sizeof(float), st), "cudaMallocAsync(wrapper images)")) return -1;
-            int rc = cuda_ok(cudaMemcpy2DAsync(d, static_cast<size_t>(cols) * sizeof(float), in, static_cast<size_t>(stride) * sizeof(float),
-                                               static_cast<size_t>(cols) * sizeof(float), rows, cudaMemcpyHostToDevice, st), "H2D") ? 0 : -1;
+            cudaEvent_t ev = nullptr;
+            int rc = cuda_ok(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event") ? 0 : -1;
+            if (rc == 0) {
+                cudaEventRecord(ev, st);                       // the allocation (stream ordered) precedes the first copy
+                cudaStreamWaitEvent(P.s_in, ev, 0);
+            }
+            int u = 0;
+            for (int r0 = 0; r0 < rows && rc == 0; r0 += rows_b, ++u) {
+                const int s = u % sge::Pipeline::kSlots, nr = std::min(rows_b, rows - r0);
+                if (!P.h2d(s, d + static_cast<size_t>(r0) * cols, cols, in + static_cast<size_t>(r0) * stride, stride, cols, nr)) rc = -1;
+                cudaEventRecord(P.e_in[s], P.s_in);
+            }
             Comp dc[3];
             for (int i = 0; i < n; ++i) dc[i] = Comp{comps[i].dx, comps[i].dy, d + (i + 1) * img};
-            if (rc == 0) rc = run_components(hx, hy, order, d, rows, cols, cols, delta_x, delta_y, boundary, dc, n);
+            if (rc == 0) {
+                cudaEventRecord(ev, P.s_in);
+                cudaStreamWaitEvent(st, ev, 0);
+                rc = run_components(hx, hy, order, d, rows, cols, cols, delta_x, delta_y, boundary, dc, n);
+                cudaEventRecord(ev, st);
+                cudaStreamWaitEvent(P.s_out, ev, 0);
+            }
             // VALID defines the interior only, and the reference leaves the border of the output untouched
             const int oy = boundary == SAVGOL2D_BOUNDARY_VALID ? hy : 0, ox = boundary == SAVGOL2D_BOUNDARY_VALID ? hx : 0;
+            const int orows = rows - 2 * oy, ocols = cols - 2 * ox;
             for (int i = 0; i < n && rc == 0; ++i)
-                rc = cuda_ok(cudaMemcpy2DAsync(comps[i].out + static_cast<size_t>(oy) * stride + ox, static_cast<size_t>(stride) * sizeof(float),
-                                               dc[i].out + static_cast<size_t>(oy) * cols + ox, static_cast<size_t>(cols) * sizeof(float),
-                                               static_cast<size_t>(cols - 2 * ox) * sizeof(float), rows - 2 * oy, cudaMemcpyDeviceToHost, st), "D2H") ? 0 : -1;
+                for (int r0 = 0; r0 < orows && rc == 0; r0 += rows_b, ++u) {
+                    const int s = u % sge::Pipeline::kSlots, nr = std::min(rows_b, orows - r0);
+                    if (!P.reuse(s) ||
+                        !P.d2h(s, comps[i].out + static_cast<size_t>(oy + r0) * stride + ox, stride,
+                               dc[i].out + static_cast<size_t>(oy + r0) * cols + ox, cols, ocols, nr)) rc = -1;
+                    cudaEventRecord(P.e_out[s], P.s_out);
+                }
+            if (!P.finish()) rc = -1;
             if (!cuda_ok(cudaStreamSynchronize(st), "sync")) rc = -1;
+            if (ev) cudaEventDestroy(ev);
             cudaFreeAsync(d, st);
             return rc;
         }
