@@ -437,11 +437,12 @@ static int component(int hx, int hy, int order, int dx, int dy, const float* in,
 // The components of a gradient / Hessian share the input image and nothing else (different parities, different
 // factors).  For device images, in order of preference:
 //   1. ONE launch of the multi-output kernel (sg2d_multi.cu): the image is staged once, every component has its own
-//      accumulator ring -- half-windows <= 4, full-size boundaries, default arithmetic;
+//      accumulator ring -- half-windows <= 8, full-size boundaries, default arithmetic;
 //   2. CONCURRENT per-component launches: the first on the caller's stream, the others on side streams forked from
 //      it and joined back (one 4096^2 image gives a launch only ~1.3 work items per resident warp, so two or three
 //      launches together fill the machine, and the later reads of the image are served from L2);
-//   3. the sequential composition of the reference (host images, aliased buffers, the exact flavour).
+//   3. the sequential composition of the reference (aliased buffers, the exact flavour).
+// Host images are uploaded once (below) and then take the device path.
 // Measured on B200 (tools/r2_wrappers.py, profiles/r2_wrappers.txt).  SAVGOL_B200_WRAP_SEQ=1 forces 3,
 // SAVGOL_B200_WRAP_FUSED=0 skips 1.
 }  // extern "C"

@@ -315,3 +315,29 @@ def test_pageable_host_buffers_take_the_bounce_path_and_match_pinned_bit_for_bit
         got.append(np.concatenate(acc, axis=1))
         st.close()
     assert got[0].shape == (ch, 2 * K) and np.array_equal(bits(got[0]), bits(got[1]))
+
+
+def test_pageable_views_with_odd_offsets_and_pitches_through_the_copy_pool():
+    """The host copy pool moves rows of any width / pitch / alignment (streaming stores need an aligned body: head
+    and tail bytes are copied separately); the padding of the output buffer must stay untouched."""
+    lib = sg.lib()
+    rng = np.random.default_rng(21)
+    f = sg.SavgolFilter(9, 3, 0, 1.0, "reflect")
+    for rows, L, pitch_in, off_in, pitch_out, off_out in ((3000, 4093, 4100, 3, 4101, 2), (700, 20001, 20001, 0, 20003, 1), (1, 3_000_001, 3_000_001, 0, 3_000_001, 0)):
+        big_in = rng.standard_normal((rows, pitch_in + 4)).astype(np.float32)
+        big_out = np.full((rows, pitch_out + 4), 7.0, np.float32)
+        x = big_in[:, off_in:off_in + L]
+        y = big_out[:, off_out:off_out + L]
+        assert lib.savgol_apply_batch(f.handle, x.ctypes.data, y.ctypes.data, rows, L, big_in.shape[1], big_out.shape[1]) == 0
+        want = f.apply(torch.from_numpy(np.ascontiguousarray(x)).cuda()).cpu().numpy()
+        assert np.array_equal(bits(y), bits(want)), (rows, L)
+        assert np.all(big_out[:, :off_out] == 7.0) and np.all(big_out[:, off_out + L:] == 7.0)
+    # 2D: a pitched pageable image batch
+    g = sg.Savgol2DFilter(4, 4, 3)
+    big = rng.random((4, 1500, 1203)).astype(np.float32)
+    outb = np.full_like(big, 7.0)
+    imgs, outs = big[:, :, 1:1201], outb[:, :, 2:1202]
+    assert lib.savgol2d_apply_batch(g.handle, imgs.ctypes.data, 1500, 1200, 1203, 1500 * 1203, outs.ctypes.data, 1203, 1500 * 1203, 4, 2) == 0
+    want = g.apply(torch.from_numpy(np.ascontiguousarray(imgs)).cuda(), "reflect").cpu().numpy()
+    assert np.array_equal(bits(outs), bits(want))
+    assert np.all(outb[:, :, :2] == 7.0) and np.all(outb[:, :, 1202:] == 7.0)
