@@ -242,6 +242,9 @@ def test_gradient_and_hessian_run_as_one_multi_output_launch():
     """Half-windows <= 8: the components share ONE launch of the multi-output kernel (sg2d_multi.cu) -- the image is staged
     once, each component has its own accumulator ring.  Same factors, same operation order per component as the
     single filters: bit-identical results.  ref: src/savgol2d.c:462-558 (one savgol2d_apply per component)."""
+    import os
+    if os.environ.get("SAVGOL_B200_WRAP_FUSED") == "0" or os.environ.get("SAVGOL_B200_WRAP_SEQ") == "1":
+        pytest.skip("multi-output launches switched off by the environment")
     lib = sg.lib()
     g = torch.Generator(device="cuda").manual_seed(33)
     for rows, cols in ((257, 1031), (1024, 1024), (64, 130)):
