@@ -509,9 +509,15 @@ __global__ void __launch_bounds__(kThreads, SG_MIN_BLOCKS) sg1d_kernel(const __g
                 auto xs = [&](int k) { const int pos = kSeg + lane + k + DELTA; return bf[pos + 4 * (pos >> 5)]; };
                 float v;
                 if constexpr (ARITH == ARITH_FAST) {
-                    v = fmaf(W.ws_first, xs(0), 0.0f);
-#pragma unroll 4
-                    for (int k = 1; k < WS; ++k) v = fmaf(W.pw[k].x, xs(k), v);
+                    // fully unrolled: the weights become constant-bank operands and the shared-memory address of tap k is
+                    // base + k + 4 * ((r + k) >> 5) (one pad chunk per 32 samples; r = the lane's position inside its group)
+                    const int q0 = DELTA + lane, r = q0 & 31;
+                    const float* b0 = bf + (kSeg + q0) + 4 * ((kSeg + q0) >> 5);
+                    v = 0.0f;
+                    static_for<WS>([&](auto kc) {
+                        constexpr int k = decltype(kc)::value;
+                        v = fmaf(k == 0 ? W.ws_first : W.pw[k].x, b0[k + 4 * ((r + k) >> 5)], v);
+                    });
                 } else {
                     v = __fmul_rn(dot_ordered<WS, ARITH>([&](int k) { return W.w[k]; }, xs), a.scale);
                 }

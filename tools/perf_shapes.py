@@ -7,7 +7,7 @@ import savgol_b200 as sg
 
 f = sg.SavgolFilter(16, 3, 1, 1.0, "reflect")
 total = 1 << 28
-for L, pitch in [(4096, 4096), (4097, 4097), (4096, 4100), (4095, 4095), (5000, 5000), (1024, 1024), (1000, 1000), (512, 512),
+for L, pitch in [(4096, 4096), (4097, 4097), (4096, 4100), (4095, 4095), (5000, 5000), (2060, 2060), (1040, 1040), (1024, 1024), (1000, 1000), (512, 512),
                  (360, 360), (256, 256), (250, 250), (128, 128), (100, 101), (64, 64), (48, 48), (33, 33), (65536, 65536), (1 << 20, 1 << 20)]:
     rows = max(1, total // L)
     x = torch.randn(rows, pitch, device="cuda")[:, :L]
