@@ -345,3 +345,23 @@ def test_single_large_host_image_travels_in_row_bands_and_matches_the_device_res
     z = img.copy()
     f.apply(z, "reflect", out=z)
     assert np.array_equal(bits(z), bits(want))
+
+
+def test_wrappers_on_degenerate_image_shapes():
+    """Tiny and skinny images: narrower than a strip, narrower than 4 columns (the separable kernels need 4), a single
+    window.  Device and host images; every component equals its single filter."""
+    g = torch.Generator(device="cuda").manual_seed(44)
+    for rows, cols in ((3, 5), (5, 3), (7, 4), (3, 3), (1, 9), (9, 1), (40, 2), (2, 40), (33, 129)):
+        img = torch.rand(rows, cols, device="cuda", generator=g)
+        himg = img.cpu().numpy()
+        for hw, order, b in ((1, 2, "constant"), (1, 2, "reflect"), (2, 3, "constant")):
+            gx, gy = sg.gradient(img, hw, hw, order, 1.0, 1.0, b)
+            hs = sg.hessian(img, hw, hw, order, 1.0, 1.0, b)
+            hgx, hgy = sg.gradient(himg, hw, hw, order, 1.0, 1.0, b)
+            for got, hgot, (dx, dy) in ((gx, hgx, (1, 0)), (gy, hgy, (0, 1)), (hs[0], None, (2, 0)), (hs[1], None, (1, 1)), (hs[2], None, (0, 2))):
+                f = sg.Savgol2DFilter(hw, hw, order, dx, dy)
+                want = f.apply(img, b)
+                assert torch.equal(got, want), (rows, cols, hw, order, b, dx, dy)
+                if hgot is not None:
+                    assert np.array_equal(bits(hgot), bits(want.cpu().numpy())), (rows, cols, hw, "host")
+                f.close()
