@@ -66,5 +66,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         print(f"[{tag:12s}] 2D {name} of one host 4096x4096 image: pinned {tp:8.3f} ms | pageable {tg:8.3f} ms", flush=True)
     sys.exit(0)
 
-for tag, env in (("adaptive", {}), ("one chunk", {"SAVGOL_B200_NO_HOST_BANDS": "1", "SAVGOL_B200_FIXED_CHUNK": "1", "SAVGOL_B200_WRAP_SEQ": "1"})):
+modes = [("adaptive", {}), ("one chunk", {"SAVGOL_B200_NO_HOST_BANDS": "1", "SAVGOL_B200_FIXED_CHUNK": "1", "SAVGOL_B200_WRAP_SEQ": "1"})]
+if len(sys.argv) > 1 and sys.argv[1] == "zerocopy":
+    modes = [("adaptive", {}), ("zero copy", {"SAVGOL_B200_ZEROCOPY": "1"})]
+for tag, env in modes:
     subprocess.run([sys.executable, os.path.abspath(__file__), "child", tag], env=dict(os.environ, **env), check=False)
