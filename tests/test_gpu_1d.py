@@ -358,3 +358,30 @@ def test_short_misaligned_rows_in_the_packed_kernel(oracle, n, m, d):
     parts.append(out[:, :cnt].cpu().numpy())
     got = np.concatenate(parts, axis=1)
     assert got.shape == want.shape and np.max(np.abs(got - want)) <= parity_tol(sig, 1.0)
+
+
+@pytest.mark.parametrize("n,m,d", [(10, 2, 1), (32, 4, 2)])
+def test_stream_chunks_with_short_tails_and_misaligned_views(oracle, n, m, d):
+    """Multichannel stream chunks whose length ends just behind a full segment (tail folded into the last segment,
+    carried state written from the staged samples) and chunks that are misaligned views: concatenated outputs equal the
+    scalar stream of the oracle."""
+    rng = np.random.default_rng(900 + n)
+    C_ = 19
+    for chunks, off in (((1025, 1040, 1056, 1057, 2080), 0), ((1030, 1031, 2049, 1024), 1), ((4097, 1056), 3)):
+        total = sum(chunks)
+        sig = rng.standard_normal((C_, total + 8)).astype(np.float32)
+        dsig = torch.from_numpy(sig).cuda()
+        o = oracle.Filter1D(n, m, d, 1.0)
+        want = np.stack([o.stream_run(r[off:off + total]) for r in sig])
+        st = sg.SavgolMCStream(C_, n, m, d, 1.0)
+        parts, pos = [], off
+        for K in chunks:
+            out, cnt = st.push(dsig[:, pos:pos + K])
+            parts.append(out[:, :cnt].cpu().numpy())
+            pos += K
+        out, cnt = st.flush(dsig)
+        parts.append(out[:, :cnt].cpu().numpy())
+        got = np.concatenate(parts, axis=1)
+        assert got.shape == want.shape, (chunks, off)
+        assert np.max(np.abs(got - want)) <= parity_tol(sig, 1.0), (chunks, off)
+        st.close()
