@@ -385,3 +385,32 @@ def test_stream_chunks_with_short_tails_and_misaligned_views(oracle, n, m, d):
         assert got.shape == want.shape, (chunks, off)
         assert np.max(np.abs(got - want)) <= parity_tol(sig, 1.0), (chunks, off)
         st.close()
+
+
+def test_halo_slices_fast_flavour_misaligned_with_tails(oracle):
+    """Default arithmetic: slices of a long signal with explicit halos, cut so that the slices are misaligned and end
+    just behind a full segment (per-row phase + tail with lhalo / rhalo), reassemble the whole-signal result bit for
+    bit and match the oracle."""
+    rng = np.random.default_rng(13)
+    L = 30011
+    x = rng.standard_normal(L).astype(np.float32)
+    xd = torch.from_numpy(x).cuda()
+    for n, m, d in ((16, 3, 1), (5, 2, 0), (32, 4, 2)):
+        for mode in MODES:
+            f = sg.SavgolFilter(n, m, d, 1.0, mode)
+            ref = oracle.Filter1D(n, m, d, 1.0, mode).apply(x)
+            whole = f.apply(xd)
+            cuts = [0, 4097, 4097 + 1031, 4097 + 1031 + 2061, 12001, 12001 + 1056, 20003, L]
+            out = torch.full_like(xd, 7.0)
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                if mode == "periodic":
+                    left = xd[a - n:a] if a > 0 else xd[L - n:]
+                    right = xd[b:b + n] if b < L else xd[:n]
+                else:
+                    left = xd[a - n:a] if a > 0 else None
+                    right = xd[b:b + n] if b < L else None
+                f.apply_halo(xd[a:b], left.contiguous() if left is not None else None,
+                             right.contiguous() if right is not None else None, out=out[a:b])
+            assert np.max(np.abs(out.cpu().numpy() - ref)) <= parity_tol(x, 1.0), (n, mode)
+            assert torch.equal(out.view(torch.int32), whole.view(torch.int32)), (n, mode)
+            f.close()
