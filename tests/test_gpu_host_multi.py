@@ -341,3 +341,17 @@ def test_pageable_views_with_odd_offsets_and_pitches_through_the_copy_pool():
     want = g.apply(torch.from_numpy(np.ascontiguousarray(imgs)).cuda(), "reflect").cpu().numpy()
     assert np.array_equal(bits(outs), bits(want))
     assert np.all(outb[:, :, :2] == 7.0) and np.all(outb[:, :, 1202:] == 7.0)
+
+
+def test_large_host_images_over_a_device_list_take_the_band_path_concurrently():
+    """savgol2d_apply_batch_multi with one large image per device thread: every thread cuts its image into row bands
+    through its own pipeline; same numbers as the device path."""
+    lib = sg.lib()
+    rng = np.random.default_rng(31)
+    imgs = rng.random((3, 2048, 2304), dtype=np.float32)
+    out = np.empty_like(imgs)
+    f = sg.Savgol2DFilter(7, 7, 3)
+    devs = (C.c_int * 3)(0, 0, 0)
+    assert lib.savgol2d_apply_batch_multi(f.handle, imgs.ctypes.data, 2048, 2304, 2304, 2048 * 2304, out.ctypes.data, 2304, 2048 * 2304, 3, 2, devs, 3) == 0
+    want = f.apply(torch.from_numpy(imgs).cuda(), "reflect").cpu().numpy()
+    assert np.array_equal(bits(out), bits(want))
