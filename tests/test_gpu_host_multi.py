@@ -355,3 +355,33 @@ def test_large_host_images_over_a_device_list_take_the_band_path_concurrently():
     assert lib.savgol2d_apply_batch_multi(f.handle, imgs.ctypes.data, 2048, 2304, 2304, 2048 * 2304, out.ctypes.data, 2304, 2048 * 2304, 3, 2, devs, 3) == 0
     want = f.apply(torch.from_numpy(imgs).cuda(), "reflect").cpu().numpy()
     assert np.array_equal(bits(out), bits(want))
+
+
+@pytest.mark.timeout(300)
+def test_host_copy_pool_under_contention():
+    """Eight host threads hammer the pageable path (shared copy pool, leased pipelines) with calls of different
+    sizes; every result must equal the single-threaded one."""
+    import threading
+
+    lib = sg.lib()
+    rng = np.random.default_rng(41)
+    f = sg.SavgolFilter(6, 2, 0, 1.0, "constant")
+    shapes = [(300, 1100), (64, 4096), (2000, 777), (17, 70001), (1200, 1024), (5, 400000), (900, 2049), (128, 8192)]
+    ins = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    want = [f.apply(torch.from_numpy(a).cuda()).cpu().numpy() for a in ins]
+    bad = []
+
+    def work(i):
+        a = ins[i]
+        out = np.empty_like(a)
+        for _ in range(12):
+            out.fill(np.nan)
+            rc = lib.savgol_apply_batch(f.handle, a.ctypes.data, out.ctypes.data, a.shape[0], a.shape[1], a.shape[1], a.shape[1])
+            if rc != 0 or not np.array_equal(bits(out), bits(want[i])):
+                bad.append(i)
+                return
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(shapes))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not bad, bad
