@@ -145,9 +145,30 @@ __device__ __forceinline__ void static_switch(int v, F&& f)
 // output registers into local memory -- an STL.128 per row on the hot path)
 template <int RX>
 struct RowVals { float2 v[RX / 2]; };
+// Out of line (the hot loop only pays the call): rows that cannot take the 16-byte store -- the ragged first / last
+// strip, and every strip of an image whose row pitch is not a multiple of 4 floats (the alignment then rotates from
+// row to row).  Lanes that lie inside the stored region still use the widest stores their address allows.
 template <int RX>
 __device__ __noinline__ void emit_ragged(float* dst_row, RowVals<RX> r, int X, int Xlo, int Xhi)
 {
+    if (X >= Xlo && X + RX <= Xhi) {
+        const bool a8 = (reinterpret_cast<uintptr_t>(dst_row) & 7) == 0;
+        if constexpr (RX == 4) {
+            if (a8) {
+                *reinterpret_cast<float2*>(dst_row) = r.v[0];
+                *reinterpret_cast<float2*>(dst_row + 2) = r.v[1];
+            } else {
+                dst_row[0] = r.v[0].x;
+                *reinterpret_cast<float2*>(dst_row + 1) = make_float2(r.v[0].y, r.v[1].x);
+                dst_row[3] = r.v[1].y;
+            }
+            return;
+        } else if constexpr (RX == 2) {
+            if (a8) *reinterpret_cast<float2*>(dst_row) = r.v[0];
+            else { dst_row[0] = r.v[0].x; dst_row[1] = r.v[0].y; }
+            return;
+        }
+    }
 #pragma unroll
     for (int j = 0; j < RX; ++j)
         if (X + j >= Xlo && X + j < Xhi) dst_row[j] = (j & 1) ? r.v[j / 2].y : r.v[j / 2].x;
