@@ -251,6 +251,10 @@ unsigned long long savgol_b200_tma_launch_count(void);
 /* Experiment / test switch for the above (process-wide): 0 never, 1 (default) where they measured faster
  * (half-windows up to 17, launches of >= 2048 segments), 2 wherever the data layout allows. */
 void savgol_b200_set_tma(int how);
+/* Host-side building block of the pageable-memory path, exported for the CPU test-suite: copies `rows` rows of
+ * `width` BYTES (pitches in bytes) with the library's host copy pool (streaming stores, several threads); returns
+ * the number of threads a large copy uses (SAVGOL_B200_COPY_THREADS).  Needs no GPU. */
+int savgol_b200_host_copy2d(void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width, size_t rows);
 /* Arithmetic flavour: 0 (default) = FMA chains, within 1e-6*max|x|/dt^d of the
  * reference; 1 = "exact": the reference's own summation order with unfused
  * multiply/add, bit-identical to the reference C code (slower; for verification). */

@@ -269,3 +269,41 @@ def test_2d_additive_plans():
         assert lib.savgol2d_b200_plan_kind(f.handle) == kind, args
         f.close()
     assert lib.savgol2d_b200_plan_kind(None) == -1
+
+
+def test_host_copy_pool_moves_rows_of_any_shape_and_alignment():
+    """The pageable-memory path of the host staging (csrc/host_stage.cu) rests on a multi-threaded 2D copy with
+    streaming stores; it needs no GPU.  Random widths / pitches / byte offsets, sizes below and above the point where
+    the pool takes over, concurrent callers."""
+    import threading
+
+    import savgol_b200 as sg
+    lib = sg.lib()
+    rng = np.random.default_rng(8)
+    cases = [(1, 1), (3, 17), (1, 300_001), (700, 4093), (64, 70_001), (5, 3_000_001), (2000, 1024), (1, 16 << 20)]
+    for rows, width in cases:
+        for so, do in ((0, 0), (1, 3), (5, 2)):
+            sp, dp = width + int(rng.integers(0, 40)), width + int(rng.integers(0, 40))
+            src = rng.integers(0, 256, rows * sp + 64, dtype=np.uint8)
+            dst = np.full(rows * dp + 64, 0xAB, np.uint8)
+            n = lib.savgol_b200_host_copy2d(dst.ctypes.data + do, dp, src.ctypes.data + so, sp, width, rows)
+            assert n >= 1
+            want = np.full_like(dst, 0xAB)
+            for r in range(rows):
+                want[do + r * dp:do + r * dp + width] = src[so + r * sp:so + r * sp + width]
+            assert np.array_equal(dst, want), (rows, width, so, do)
+    # concurrent callers share the pool
+    srcs = [rng.integers(0, 256, 6_000_000 + 1000 * i, dtype=np.uint8) for i in range(6)]
+    dsts = [np.zeros_like(a) for a in srcs]
+
+    def work(i):
+        for _ in range(10):
+            dsts[i][:] = 0
+            lib.savgol_b200_host_copy2d(dsts[i].ctypes.data, srcs[i].size, srcs[i].ctypes.data, srcs[i].size, srcs[i].size, 1)
+            assert np.array_equal(dsts[i], srcs[i])
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(6)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert all(np.array_equal(d, s_) for d, s_ in zip(dsts, srcs))
+    assert lib.savgol_b200_host_copy2d(None, 0, None, 0, 0, 0) >= 1
