@@ -255,6 +255,15 @@ void savgol_b200_set_tma(int how);
  * `width` BYTES (pitches in bytes) with the library's host copy pool (streaming stores, several threads); returns
  * the number of threads a large copy uses (SAVGOL_B200_COPY_THREADS).  Needs no GPU. */
 int savgol_b200_host_copy2d(void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width, size_t rows);
+/* How the library would dispatch a 1D launch of `rows` contiguous-sample rows of `length` floats with `row_pitch`
+ * floats between rows, the first sample `first_sample_offset` floats behind a 16-byte boundary -- pure host logic, no
+ * GPU needed (CPU test-suite, tools).  *family: 0 generic cp.async kernel, 1 short-row kernel (several rows per warp),
+ * 2 bulk-tensor (TMA) kernel; *lanes_per_row: short-row kernel only; *phase: rows are cut on a per-row alignment
+ * phase; *tail: the last full segment also produces the <= 32 outputs behind it; *segments_per_row: 1024-output work
+ * items per row.  Returns the internal instantiation index (>= 0) or -1 on bad arguments. */
+int savgol_b200_plan_1d(int half_window, int stream_variant, int exact, size_t rows, size_t length, size_t row_pitch,
+                        size_t first_sample_offset, int polynomial_edges, int *family, int *lanes_per_row, int *phase,
+                        int *tail, long long *segments_per_row);
 /* Arithmetic flavour: 0 (default) = FMA chains, within 1e-6*max|x|/dt^d of the
  * reference; 1 = "exact": the reference's own summation order with unfused
  * multiply/add, bit-identical to the reference C code (slower; for verification). */

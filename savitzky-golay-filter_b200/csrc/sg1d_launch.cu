@@ -191,14 +191,16 @@ static cudaError_t sg1d_launch_tma(EncodeTiled enc, int n, int vt, const W1D& w,
     return cudaGetLastError();
 }
 
-cudaError_t sg1d_launch(int n, int variant, const W1D& w, Args1D& a, cudaStream_t stream)
+// Which kernel family / instantiation serves a launch, and its work decomposition -- pure host logic (no CUDA call), so
+// the CPU test-suite can check it (savgol_b200_plan_1d).  Fills the dispatch fields of `a`.
+Plan1D sg1d_plan(int n, int variant, Args1D& a, bool allow_tma)
 {
-    if (n < 1 || n > kMaxN || variant < 0 || variant >= V_COUNT) return cudaErrorInvalidValue;
+    Plan1D p{};
+    p.family = PLAN_GENERIC;
     // short rows (<= 512 samples): several rows per warp instead of idle lanes
-    int gi_idx = 0;
-    size_t smem = 0;
     a.pack_g = 0;
     a.tail = a.phase = 0;
+    a.out_tma = 0;
     // contiguous rows that are not all 16-byte aligned: row slots / segments start on a per-row phase (up to 3 outputs
     // early in the short-row kernel, up to kPhase-1 in the generic one) so that their chunks are aligned in memory
     const bool in_aligned = rows_aligned16(a);
@@ -212,32 +214,50 @@ cudaError_t sg1d_launch(int n, int variant, const W1D& w, Args1D& a, cudaStream_
         const bool edges = a.edge_lead || a.edge_trail;
         while (g < 16 && packed_smem_bytes(n, variant == V_STREAM_FAST, g, edges) > kPackedSmemMax) g *= 2;
         a.pack_g = g;
-        gi_idx = (g == 1 ? 0 : g == 2 ? 1 : g == 4 ? 2 : g == 8 ? 3 : 4) + (edges ? 5 : 0);
-        smem = packed_smem_bytes(n, variant == V_STREAM_FAST, g, edges);
-        variant = variant == V_BATCH_FAST ? (phase ? V_PACK_BATCH_FAST_PH : V_PACK_BATCH_FAST) : (phase ? V_PACK_STREAM_FAST_PH : V_PACK_STREAM_FAST);
-    } else if (variant >= V_PACK_BATCH_FAST) {
-        return cudaErrorInvalidValue;
+        p.family = PLAN_PACKED;
+        p.gi_idx = (g == 1 ? 0 : g == 2 ? 1 : g == 4 ? 2 : g == 8 ? 3 : 4) + (edges ? 5 : 0);
+        p.smem = packed_smem_bytes(n, variant == V_STREAM_FAST, g, edges);
+        p.variant = variant == V_BATCH_FAST ? (phase ? V_PACK_BATCH_FAST_PH : V_PACK_BATCH_FAST) : (phase ? V_PACK_STREAM_FAST_PH : V_PACK_STREAM_FAST);
+        a.tiles_per_row = 1;
+        return p;
     }
-    a.out_tma = 0;
-    if (a.pack_g == 0 && tma_eligible(n, variant, a)) {
-        if (EncodeTiled enc = encode_tiled()) {
-            const cudaError_t e = sg1d_launch_tma(enc, n, variant == V_STREAM_FAST ? VT_STREAM : VT_BATCH, w, a, stream);
-            if (e != cudaErrorNotSupported) return e;   // NotSupported: the driver refused a tensor map -> generic kernel
-        }
+    p.variant = variant;
+    if (allow_tma && tma_eligible(n, variant, a)) {
+        p.family = PLAN_TMA;
+        a.tiles_per_row = (a.len + kTile - 1) / kTile;
+        return p;
     }
     // generic kernel: misaligned rows / short tails take the PT instantiation of the FAST flavours (the exact flavours
     // stage misaligned rows with 4-byte copies, as before)
-    if (a.pack_g == 0 && (variant == V_BATCH_FAST || variant == V_STREAM_FAST)) {
+    if (variant == V_BATCH_FAST || variant == V_STREAM_FAST) {
         const long long span = a.len + (phase ? kPhase - 1 : 0);
         a.phase = phase ? 1 : 0;
         a.tiles_per_row = (span + kTile - 1) / kTile;
         // a last segment of <= kTail outputs would cost a whole pass of its warp: the segment before it takes them
         a.tail = short_tail(a) ? 1 : 0;
         if (a.tail) --a.tiles_per_row;
-        if (a.phase || a.tail) variant = variant == V_BATCH_FAST ? V_BATCH_FAST_PT : V_STREAM_FAST_PT;
-    } else if (a.pack_g == 0) {
+        if (a.phase || a.tail) p.variant = variant == V_BATCH_FAST ? V_BATCH_FAST_PT : V_STREAM_FAST_PT;
+    } else {
         a.tiles_per_row = (a.len + kTile - 1) / kTile;
     }
+    return p;
+}
+
+cudaError_t sg1d_launch(int n, int variant, const W1D& w, Args1D& a, cudaStream_t stream)
+{
+    if (n < 1 || n > kMaxN || variant < 0 || variant >= V_COUNT) return cudaErrorInvalidValue;
+    if (variant >= V_PACK_BATCH_FAST) return cudaErrorInvalidValue;   // callers name the base flavours only
+    Plan1D p = sg1d_plan(n, variant, a, true);
+    if (p.family == PLAN_TMA) {
+        if (EncodeTiled enc = encode_tiled()) {
+            const cudaError_t e = sg1d_launch_tma(enc, n, variant == V_STREAM_FAST ? VT_STREAM : VT_BATCH, w, a, stream);
+            if (e != cudaErrorNotSupported) return e;   // NotSupported: the driver refused a tensor map -> generic kernel
+        }
+        p = sg1d_plan(n, variant, a, false);
+    }
+    const int gi_idx = p.gi_idx;
+    const size_t smem = p.smem;
+    variant = p.variant;
     const Kernel1D& k = sg1d_group_table((n - 1) / 4)[((n - 1) % 4) * V_COUNT + variant];
 
     int dev = 0;
@@ -286,3 +306,28 @@ cudaError_t sg1d_launch(int n, int variant, const W1D& w, Args1D& a, cudaStream_
 }
 
 }  // namespace sg
+
+// Dispatch of a 1D launch as the library would decide it, without touching the GPU (include/savgol_b200.h).
+extern "C" int savgol_b200_plan_1d(int half_window, int stream_variant, int exact, size_t rows, size_t length, size_t row_pitch,
+                                   size_t first_sample_offset, int polynomial_edges, int* family, int* lanes_per_row, int* phase,
+                                   int* tail, long long* segments_per_row)
+{
+    using namespace sg;
+    if (half_window < 1 || half_window > kMaxN || rows == 0 || length == 0 || row_pitch < length) return -1;
+    Args1D a{};
+    a.in = reinterpret_cast<const char*>(static_cast<uintptr_t>(0x100000) + 4 * first_sample_offset);   // only its alignment matters
+    a.out = reinterpret_cast<char*>(static_cast<uintptr_t>(0x40000000) + 4 * first_sample_offset);
+    a.rows = static_cast<long long>(rows); a.len = a.out_len = static_cast<long long>(length);
+    a.in_row_bytes = a.out_row_bytes = static_cast<long long>(row_pitch * 4);
+    a.in_stride = a.out_stride = 4;
+    a.edge_lead = a.edge_trail = polynomial_edges ? 1 : 0;
+    const int variant = stream_variant ? (exact ? V_STREAM_EXACTSEQ : V_STREAM_FAST) : (exact ? V_BATCH_EXACT4 : V_BATCH_FAST);
+    const Plan1D p = sg1d_plan(half_window, variant, a, true);
+    if (family) *family = p.family;
+    if (lanes_per_row) *lanes_per_row = a.pack_g;
+    if (phase) *phase = a.phase;
+    if (tail) *tail = a.tail;
+    if (segments_per_row) *segments_per_row = a.tiles_per_row;
+    return p.variant;
+}
+

@@ -42,6 +42,16 @@ typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, v
                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiled encode_tiled();
 
+// Dispatch decision of one launch (sg1d_launch.cu: sg1d_plan).
+enum : int { PLAN_GENERIC = 0, PLAN_PACKED = 1, PLAN_TMA = 2 };
+struct Plan1D {
+    int family;      // PLAN_*
+    int variant;     // table column actually launched (V_*)
+    int gi_idx;      // occupancy cache slot (packed kernel: packing class x edge values)
+    size_t smem;     // dynamic shared memory (packed kernel)
+};
+Plan1D sg1d_plan(int n, int variant, Args1D& args, bool allow_tma);
+
 // Grid sizing + launch.  Returns cudaSuccess or the launch error.
 cudaError_t sg1d_launch(int n, int variant, const W1D& w, Args1D& args, cudaStream_t stream);
 

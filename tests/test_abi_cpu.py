@@ -307,3 +307,52 @@ def test_host_copy_pool_moves_rows_of_any_shape_and_alignment():
     [t.join() for t in th]
     assert all(np.array_equal(d, s_) for d, s_ in zip(dsts, srcs))
     assert lib.savgol_b200_host_copy2d(None, 0, None, 0, 0, 0) >= 1
+
+
+def test_dispatch_of_1d_launches_is_what_the_design_says():
+    """savgol_b200_plan_1d: the host logic that picks the kernel family and the work decomposition (DESIGN.md 4.1 /
+    4.2), checked without a GPU."""
+    import ctypes as C
+
+    import savgol_b200 as sg
+    lib = sg.lib()
+
+    def plan(n, rows, L, pitch=None, off=0, stream=0, exact=0, poly=0):
+        fam, g, ph, tl, spr = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_longlong()
+        v = lib.savgol_b200_plan_1d(n, stream, exact, rows, L, pitch or L, off, poly, C.byref(fam), C.byref(g), C.byref(ph), C.byref(tl), C.byref(spr))
+        assert v >= 0
+        return fam.value, g.value, ph.value, tl.value, spr.value
+
+    GENERIC, PACKED, TMA = 0, 1, 2
+    # config 2 / config 5 shapes: bulk-tensor kernels, four / one segment(s) per row
+    assert plan(16, 65536, 4096) == (TMA, 0, 0, 0, 4)
+    assert plan(10, 1 << 20, 1024, stream=1) == (TMA, 0, 0, 0, 1)
+    # wide windows and small launches keep the cp.async kernel (the measured rule of tma_eligible)
+    assert plan(32, 65536, 4096)[0] == GENERIC and plan(16, 16, 4096)[0] == GENERIC
+    assert plan(16, 65536, 4096, exact=1) == (GENERIC, 0, 0, 0, 4)
+    # misaligned rows: per-row phase, segments counted for the worst phase, short tails folded
+    assert plan(16, 65520, 4097) == (GENERIC, 0, 1, 1, 4)             # 4097 + 31 = 4 x 1024 + 32
+    assert plan(16, 65552, 4095) == (GENERIC, 0, 1, 1, 4)
+    assert plan(16, 1000, 4096, off=1) == (GENERIC, 0, 1, 1, 4)       # aligned pitch, misaligned base
+    assert plan(16, 53687, 5001) == (GENERIC, 0, 1, 0, 5)
+    assert plan(16, 1, 4097) == (GENERIC, 0, 0, 1, 4)                 # a single row only needs an aligned base
+    assert plan(16, 65536, 4100) == (GENERIC, 0, 0, 1, 4)             # aligned rows with a tail of 4: generic + tail beats 5 TMA segments
+    assert plan(16, 65536, 4096, pitch=4100) == (TMA, 0, 0, 0, 4)
+    assert plan(16, 65520, 4097, exact=1) == (GENERIC, 0, 0, 0, 5)    # the exact flavours keep the plain decomposition
+    # short rows: lanes per row by length (+3 when the rows need a phase), wider slots when shared memory runs out
+    assert plan(16, 1000, 512) == (PACKED, 16, 0, 0, 1)
+    assert plan(16, 1000, 360) == (PACKED, 16, 0, 0, 1)
+    assert plan(16, 1000, 256) == (PACKED, 8, 0, 0, 1)
+    assert plan(16, 1000, 250) == (PACKED, 8, 1, 0, 1)
+    assert plan(16, 1000, 254) == (PACKED, 16, 1, 0, 1)               # 254 + 3 > 256
+    assert plan(16, 1000, 64) == (PACKED, 2, 0, 0, 1)
+    assert plan(16, 1000, 33) == (PACKED, 2, 1, 0, 1)
+    assert plan(2, 1000, 20) == (PACKED, 1, 0, 0, 1)
+    assert plan(16, 1000, 510, off=2)[0] == GENERIC                   # 510 + 3 > 512: one generic segment on a phase
+    assert plan(16, 1, 300)[0] == GENERIC                             # a single short row is not a batch
+    assert plan(16, 1000, 513) == (GENERIC, 0, 1, 0, 1)
+    assert plan(16, 1000, 1000) == (GENERIC, 0, 0, 0, 1)
+    assert plan(16, 1000, 1001) == (GENERIC, 0, 1, 1, 1)              # 1001 + 31 = 1024 + 8: one segment + tail
+    assert plan(16, 1000, 1040) == (GENERIC, 0, 0, 1, 1)
+    assert lib.savgol_b200_plan_1d(0, 0, 0, 1, 100, 100, 0, 0, None, None, None, None, None) == -1
+    assert lib.savgol_b200_plan_1d(16, 0, 0, 1, 100, 50, 0, 0, None, None, None, None, None) == -1
