@@ -251,6 +251,9 @@ unsigned long long savgol_b200_tma_launch_count(void);
 /* Experiment / test switch for the above (process-wide): 0 never, 1 (default) where they measured faster
  * (half-windows up to 17, launches of >= 2048 segments), 2 wherever the data layout allows. */
 void savgol_b200_set_tma(int how);
+/* Floats per staging chunk of a host-pointer call that moves `total_floats` each way (pinned or pageable buffers):
+ * the configured chunk (64 MiB / 16 MiB), shrunk to ~1/8 (1/4) of calls of 8 MiB and more, never below 2 MiB. */
+size_t savgol_b200_staging_chunk(size_t total_floats, int pageable);
 /* Host-side building block of the pageable-memory path, exported for the CPU test-suite: copies `rows` rows of
  * `width` BYTES (pitches in bytes) with the library's host copy pool (streaming stores, several threads); returns
  * the number of threads a large copy uses (SAVGOL_B200_COPY_THREADS).  Needs no GPU. */

@@ -94,6 +94,7 @@ PROTOTYPES = {
     "savgol_b200_tma_launch_count": (C.c_ulonglong, []),
     "savgol_b200_plan_1d": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int,
                                       C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
+    "savgol_b200_staging_chunk": (C.c_size_t, [C.c_size_t, C.c_int]),
     "savgol_b200_host_copy2d": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t]),
     "savgol_b200_set_tma": (None, [C.c_int]),
     "savgol_b200_set_exact": (None, [C.c_int]),

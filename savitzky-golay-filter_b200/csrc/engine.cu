@@ -240,6 +240,7 @@ void savgol_b200_set_tma(int how) { sg::g_tma_enabled.store(how < 0 ? 0 : how > 
 void savgol_b200_set_exact(int exact) { sge::t_exact = exact ? 1 : 0; }
 void savgol_b200_set_exact_default(int exact) { sge::g_exact.store(exact ? 1 : 0); }
 int savgol_b200_get_exact(void) { return sge::exact_mode(); }
+size_t savgol_b200_staging_chunk(size_t total_floats, int pageable) { return sge::staging_chunk(total_floats, pageable != 0); }
 int savgol_b200_host_copy2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width, size_t rows)
 {
     if ((!dst || !src) && width && rows) return -1;

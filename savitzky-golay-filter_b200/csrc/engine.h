@@ -146,5 +146,6 @@ bool run1d_host_range(Pipeline& P, const SavgolFilter* f, const float* x, size_t
 bool run1d_host(const SavgolFilter* f, const float* in, float* out, size_t rows, size_t len, size_t in_pitch,
                 size_t out_pitch, int mode, bool poly_edges, int arith);
 size_t chunk_floats(bool bounce = false);
+size_t staging_chunk(size_t total, bool bounce);
 
 }  // namespace sge

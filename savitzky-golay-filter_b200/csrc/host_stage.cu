@@ -165,7 +165,13 @@ size_t Pipeline::begin(const void* in, const void* out, size_t total)
     bounce_in = !off && in && classify(in) == MemKind::Pageable;
     bounce_out = !off && out && classify(out) == MemKind::Pageable;
     for (Pending& p : pend) p.dst = nullptr;
-    size_t chunk = chunk_floats(bounce_in || bounce_out);
+    return staging_chunk(total, bounce_in || bounce_out);
+}
+
+// Staging chunk (floats) of a host-pointer call of `total` floats; pure host logic (savgol_b200_staging_chunk).
+size_t staging_chunk(size_t total, bool bounce)
+{
+    size_t chunk = chunk_floats(bounce);
     static const bool fixed = [] { const char* e = getenv("SAVGOL_B200_FIXED_CHUNK"); return e && e[0] == '1'; }();
     if (total >= (size_t(8) << 18) && !fixed) {
         // measured on B200 (pinned, tools/r2_host_small.py): 64 MiB each way as one chunk 2.44 ms (H2D, kernel and D2H in
@@ -174,7 +180,7 @@ size_t Pipeline::begin(const void* in, const void* out, size_t total)
         const size_t floor_ = std::min<size_t>(chunk, size_t(2) << 18);   // 2 MiB: below that the link efficiency drops
         // (through bounce buffers every chunk also costs a wake-up of the host copy pool: four chunks, not eight --
         // 64 MiB pageable: 2.8 ms in 16 MiB chunks, 3.4 ms in 8 MiB chunks)
-        chunk = std::min(chunk, std::max(floor_, total / ((bounce_in || bounce_out) ? 4 : 8)));
+        chunk = std::min(chunk, std::max(floor_, total / (bounce ? 4 : 8)));
     }
     return chunk;
 }

@@ -356,3 +356,21 @@ def test_dispatch_of_1d_launches_is_what_the_design_says():
     assert plan(16, 1000, 1040) == (GENERIC, 0, 0, 1, 1)
     assert lib.savgol_b200_plan_1d(0, 0, 0, 1, 100, 100, 0, 0, None, None, None, None, None) == -1
     assert lib.savgol_b200_plan_1d(16, 0, 0, 1, 100, 50, 0, 0, None, None, None, None, None) == -1
+
+
+def test_staging_chunk_policy():
+    """Host-pointer calls: 64 MiB chunks (16 MiB through bounce buffers), shrunk for calls that would fit one or two
+    chunks so that upload, kernel and download overlap; small calls stay whole."""
+    import os
+
+    import savgol_b200 as sg
+    if any(os.environ.get(k) for k in ("SAVGOL_B200_CHUNK_MIB", "SAVGOL_B200_BOUNCE_MIB", "SAVGOL_B200_FIXED_CHUNK")):
+        pytest.skip("staging chunk overridden by the environment")
+    chunk = sg.lib().savgol_b200_staging_chunk
+    MiB = 1 << 18   # floats
+    assert chunk(1 << 30, 0) == 64 * MiB and chunk(1 << 30, 1) == 16 * MiB       # large calls: the configured chunk
+    assert chunk(64 * MiB, 0) == 8 * MiB and chunk(64 * MiB, 1) == 16 * MiB      # 64 MiB: eight chunks pinned, four pageable
+    assert chunk(16 * MiB, 0) == 2 * MiB and chunk(16 * MiB, 1) == 4 * MiB
+    assert chunk(8 * MiB, 0) == 2 * MiB                                            # never below 2 MiB
+    assert chunk(1_000_000, 0) == 64 * MiB and chunk(1_000_000, 1) == 16 * MiB    # under 8 MiB: one chunk (config 1)
+    assert chunk(0, 0) == 64 * MiB
