@@ -209,6 +209,9 @@ int savgol2d_hessian(int half_win_x, int half_win_y, int poly_order,
                      const float *input, int rows, int cols, int stride,
                      float *hess_xx, float *hess_xy, float *hess_yy,
                      float delta_x, float delta_y, Savgol2DBoundary boundary);
+/* Would the gradient (hessian = 0) / Hessian (1) of this configuration run as ONE multi-output launch (device images,
+ * non-overlapping equally aligned outputs, full-size boundary, default arithmetic)?  1 yes, 0 no, -1 invalid.  Host logic. */
+int savgol2d_b200_wrapper_plan(int half_win_x, int half_win_y, int poly_order, int hessian);
 int savgol2d_laplacian(int half_win_x, int half_win_y, int poly_order,
                        const float *input, int rows, int cols, int stride,
                        float *output,

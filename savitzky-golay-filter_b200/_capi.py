@@ -117,6 +117,7 @@ PROTOTYPES = {
                                        C.c_size_t, C.c_size_t, C.c_int]),
     "savgol2d_b200_plan": (C.c_int, [F2, C.POINTER(C.c_int), C.POINTER(C.c_float)]),
     "savgol2d_b200_plan_kind": (C.c_int, [F2]),
+    "savgol2d_b200_wrapper_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "savgol2d_apply_band": (C.c_int, [F2, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "savgol2d_apply_band_at": (C.c_int, [F2, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "savgol_b200_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]),

@@ -597,6 +597,30 @@ int run_components(int hx, int hy, int order, const float* in, int rows, int col
 }  // namespace
 extern "C" {
 
+// Would savgol2d_gradient (hessian = 0) / savgol2d_hessian (1) run all components of this configuration in ONE multi-output
+// launch -- for device images with non-overlapping, equally aligned outputs, a full-size boundary and the default
+// arithmetic?  Pure host logic (CPU test-suite).  1 yes, 0 per-component launches, -1 invalid configuration.
+int savgol2d_b200_wrapper_plan(int hx, int hy, int order, int hessian)
+{
+    if (hessian && order < 2) return -1;
+    const Comp grad[2] = {{1, 0, nullptr}, {0, 1, nullptr}}, hess[3] = {{2, 0, nullptr}, {1, 1, nullptr}, {0, 2, nullptr}};
+    const Comp* comps = hessian ? hess : grad;
+    const int n = hessian ? 3 : 2;
+    const sg2d::SepPlan* plans[3] = {nullptr, nullptr, nullptr};
+    for (int i = 0; i < n; ++i) {
+        Savgol2DFilter* f = component_filter(hx, hy, order, comps[i].dx, comps[i].dy, 1.0f, 1.0f);
+        if (!f) return -1;
+        const Filter2DImpl* fi = live2d(f);
+        if (!fi) return -1;
+        plans[i] = &fi->plan;
+    }
+    sg2d::Args2D a{};
+    a.rows = 64; a.cols = 64;
+    a.out = reinterpret_cast<float*>(static_cast<uintptr_t>(0x100000));
+    a.out1 = a.out + 64 * 64; a.out2 = a.out1 + 64 * 64;
+    return sg2d::multi_supported(a, plans, n) ? 1 : 0;
+}
+
 int savgol2d_gradient(int hx, int hy, int order, const float* input, int rows, int cols, int stride,
                       float* grad_x, float* grad_y, float delta_x, float delta_y, Savgol2DBoundary boundary)
 {

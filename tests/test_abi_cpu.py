@@ -374,3 +374,20 @@ def test_staging_chunk_policy():
     assert chunk(8 * MiB, 0) == 2 * MiB                                            # never below 2 MiB
     assert chunk(1_000_000, 0) == 64 * MiB and chunk(1_000_000, 1) == 16 * MiB    # under 8 MiB: one chunk (config 1)
     assert chunk(0, 0) == 64 * MiB
+
+
+def test_gradient_and_hessian_take_one_launch_for_half_windows_up_to_8():
+    """savgol2d_b200_wrapper_plan: which wrapper configurations have a multi-output kernel (csrc/sg2d_multi.cu) --
+    half-windows <= 8 and 1..3 (gradient) / 1..2 (Hessian) separable factors per component."""
+    import savgol_b200 as sg
+    plan = sg.lib().savgol2d_b200_wrapper_plan
+    for hw in range(1, 9):
+        for order in range(1, min(5, 2 * hw) + 1):
+            assert plan(hw, hw, order, 0) == 1, (hw, order)
+            if order >= 2:
+                assert plan(hw, hw, order, 1) == 1, (hw, order)
+    assert plan(3, 2, 3, 0) == 1 and plan(2, 7, 2, 1) == 1          # rectangular windows
+    assert plan(9, 9, 3, 0) == 0 and plan(12, 12, 2, 1) == 0        # wider windows: per-component launches
+    assert plan(9, 3, 2, 0) == 0
+    assert plan(2, 2, 1, 1) == -1                                   # a Hessian needs order >= 2 (ref: src/savgol2d.c:507-510)
+    assert plan(2, 2, 9, 0) == -1                                   # invalid configuration
